@@ -1,0 +1,19 @@
+"""Register the hyphenated package directory ``mp-mvs_b200/`` as module ``mpmvs_b200``."""
+import importlib.util
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG_DIR = os.path.join(ROOT, "mp-mvs_b200")
+
+
+def load_package():
+    if "mpmvs_b200" in sys.modules:
+        return sys.modules["mpmvs_b200"]
+    spec = importlib.util.spec_from_file_location(
+        "mpmvs_b200", os.path.join(PKG_DIR, "__init__.py"), submodule_search_locations=[PKG_DIR]
+    )
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["mpmvs_b200"] = mod
+    spec.loader.exec_module(mod)
+    return mod
