@@ -1,0 +1,758 @@
+// pm_capi.cu -- implementation of the C ABI declared in include/mpmvs_b200.h.
+//
+// Host-side counterpart of the members the reference defines in src/PatchMatch.cpp:640-1139
+// (PatchMatchInit / AllocatePatchMatch / CudaMemInit / CudaPlanarPriorInitialization / Release /
+// getters) and of the launcher PatchMatchCUDA::Run (src/PatchMatch.cu:1188-1254), redesigned:
+//   * all images of a GPU live in ONE layered float texture (mpmvs_image_cache); a problem only
+//     records layer indices -- no per-problem cudaMallocArray / texture creation;
+//   * per-pixel state buffers and pinned host mirrors are pooled inside the handle and reused when
+//     the next reference image has the same size;
+//   * a run is 22 launches on one stream with no host synchronisation in between (the reference
+//     calls cudaDeviceSynchronize after every launch); results come back with async copies;
+//   * source depth maps are read from linear device memory (so the buffer an NCCL all-gather fills
+//     can be used in place) instead of one cudaArray + texture per source.
+// There is no CPU fallback: without a CUDA device every entry point fails with MPMVS_E_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/mpmvs_b200.h"
+#include "pm_core.cuh"
+#include "pm_kernels.h"
+#include "pm_views.h"
+
+static_assert(sizeof(mpmvs_camera) == 112, "mpmvs_camera must stay binary compatible with struct Camera");
+static_assert(sizeof(PmView) % 4 == 0, "PmView is staged word-wise");
+
+#define CK(call)                                  \
+    do {                                          \
+        cudaError_t e_ = (call);                  \
+        if (e_ != cudaSuccess) return (int)e_;    \
+    } while (0)
+
+struct mpmvs_image_cache {
+    int device = 0;
+    int W = 0, H = 0, capacity = 0, used = 0;
+    cudaArray_t arr = nullptr;
+    cudaTextureObject_t tex = 0;
+    std::unordered_map<int, int> id2layer;
+    std::vector<int> lw, lh;  // per-layer image size
+};
+
+struct mpmvs_problem {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int n = 0, W = 0, H = 0;
+    size_t wh = 0, wh_alloc = 0;
+    mpmvs_camera cams[MPMVS_MAX_VIEWS];
+    mpmvs_image_cache* cache = nullptr;
+    bool own_cache = false;
+    int layers[MPMVS_MAX_VIEWS];
+    // PatchMatchParams mirror (include/PatchMatch.h:48-67)
+    int max_iterations = 3, top_k = 4, max_scale = 2;
+    float sigma_spatial = 5.0f, sigma_color = 3.0f;
+    bool geom = false, geomPlanarPrior = false, planar = false;
+    float depth_min = 0.f, depth_max = 1.f;
+    // device state
+    PmState S{};
+    pm_f4* d_prior = nullptr;
+    uint32_t* d_mask = nullptr;
+    PmView hviews[PM_MAX_SRC];
+    PmView* dviews = nullptr;
+    float* d_depths[PM_MAX_SRC];       // owned copies of source depth maps (host-upload path)
+    size_t d_depths_cap[PM_MAX_SRC];
+    bool has_depths = false, has_prior = false;
+    // pinned host mirrors
+    float *h_planes = nullptr, *h_costs = nullptr, *h_geom = nullptr;
+    size_t h_alloc = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int last_launches = 0;
+    bool ran = false;
+    // profiling (mpmvs_set_profiling): bit 0 = an event between all launches, bit 1 = count executed NCC evaluations
+    int profiling = 0;
+    std::vector<cudaEvent_t> pev;          // pev[0] before init, pev[1] after init, pev[2+k] after sweep k, last after finalize
+    int pev_used = 0;
+    unsigned long long* d_counters = nullptr;
+};
+
+namespace {
+
+int ensure_device(int device) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return MPMVS_E_NO_DEVICE;
+    if (device < 0 || device >= count) return MPMVS_E_ARG;
+    CK(cudaSetDevice(device));
+    return MPMVS_OK;
+}
+
+PmFrame make_frame(const mpmvs_problem* p) {
+    PmFrame F = pm_make_frame(p->cams[0], p->n, p->depth_min, p->depth_max, p->sigma_spatial, p->sigma_color, p->top_k,
+                              p->geom, p->planar);
+    F.ref_layer = p->layers[0];
+    int soft = 0;
+    for (int i = 0; i < p->n; ++i)
+        if (p->cams[i].width != p->cache->W || p->cams[i].height != p->cache->H) soft = 1;
+    F.soft_clamp = soft;
+    F.tex = (unsigned long long)p->cache->tex;
+    return F;
+}
+
+int cache_alloc(mpmvs_image_cache* c, int W, int H, int capacity) {
+    const cudaChannelFormatDesc desc = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+    CK(cudaMalloc3DArray(&c->arr, &desc, make_cudaExtent((size_t)W, (size_t)H, (size_t)capacity), cudaArrayLayered));
+    cudaResourceDesc res;
+    memset(&res, 0, sizeof(res));
+    res.resType = cudaResourceTypeArray;
+    res.res.array.array = c->arr;
+    // CudaMemInit's descriptor (PatchMatch.cpp:1012-1018): linear filter, element type, un-normalised
+    // coordinates; its Wrap mode is not defined for un-normalised coordinates and acts as clamp.
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof(td));
+    td.addressMode[0] = cudaAddressModeClamp;
+    td.addressMode[1] = cudaAddressModeClamp;
+    td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    CK(cudaCreateTextureObject(&c->tex, &res, &td, nullptr));
+    c->W = W; c->H = H; c->capacity = capacity; c->used = 0;
+    c->id2layer.clear();
+    c->lw.assign(capacity, 0);
+    c->lh.assign(capacity, 0);
+    return MPMVS_OK;
+}
+
+void cache_free(mpmvs_image_cache* c) {
+    if (c->tex) cudaDestroyTextureObject(c->tex);
+    if (c->arr) cudaFreeArray(c->arr);
+    c->tex = 0; c->arr = nullptr; c->capacity = c->used = 0;
+    c->id2layer.clear();
+}
+
+int cache_upload(mpmvs_image_cache* c, int layer, const void* src, size_t pitch, int w, int h, cudaMemcpyKind kind,
+                 cudaStream_t st) {
+    cudaMemcpy3DParms prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.srcPtr = make_cudaPitchedPtr(const_cast<void*>(src), pitch, (size_t)w, (size_t)h);
+    prm.dstArray = c->arr;
+    prm.dstPos = make_cudaPos(0, 0, (size_t)layer);
+    prm.extent = make_cudaExtent((size_t)w, (size_t)h, 1);
+    prm.kind = kind;
+    CK(cudaMemcpy3DAsync(&prm, st));
+    c->lw[layer] = w; c->lh[layer] = h;
+    return MPMVS_OK;
+}
+
+int alloc_state(mpmvs_problem* p) {
+    const size_t wh = p->wh;
+    if (wh > p->wh_alloc) {
+        cudaFree(p->S.planes); cudaFree(p->S.costs); cudaFree(p->S.views); cudaFree(p->S.rng); cudaFree(p->S.geom);
+        cudaFree(p->d_prior); cudaFree(p->d_mask);
+        p->S = PmState{}; p->d_prior = nullptr; p->d_mask = nullptr; p->wh_alloc = 0;
+        CK(cudaMalloc((void**)&p->S.planes, wh * sizeof(pm_f4)));
+        CK(cudaMalloc((void**)&p->S.costs, wh * sizeof(float)));
+        CK(cudaMalloc((void**)&p->S.views, wh * sizeof(uint32_t)));
+        CK(cudaMalloc((void**)&p->S.rng, wh * 6 * sizeof(uint32_t)));
+        CK(cudaMalloc((void**)&p->S.geom, wh * sizeof(float)));
+        CK(cudaMalloc((void**)&p->d_prior, wh * sizeof(pm_f4)));
+        CK(cudaMalloc((void**)&p->d_mask, wh * sizeof(uint32_t)));
+        p->wh_alloc = wh;
+    }
+    p->S.prior = p->d_prior;
+    p->S.mask = p->d_mask;
+    p->S.counters = nullptr;
+    CK(cudaMemsetAsync(p->S.views, 0, wh * sizeof(uint32_t), p->stream));
+    CK(cudaMemsetAsync(p->S.geom, 0, wh * sizeof(float), p->stream));
+    CK(cudaMemsetAsync(p->d_mask, 0, wh * sizeof(uint32_t), p->stream));
+    if (!p->dviews) CK(cudaMalloc((void**)&p->dviews, PM_MAX_SRC * sizeof(PmView)));
+    return MPMVS_OK;
+}
+
+int ensure_mirrors(mpmvs_problem* p) {
+    if (p->wh > p->h_alloc) {
+        cudaFreeHost(p->h_planes); cudaFreeHost(p->h_costs); cudaFreeHost(p->h_geom);
+        p->h_planes = p->h_costs = p->h_geom = nullptr; p->h_alloc = 0;
+        CK(cudaMallocHost((void**)&p->h_planes, p->wh * sizeof(pm_f4)));
+        CK(cudaMallocHost((void**)&p->h_costs, p->wh * sizeof(float)));
+        CK(cudaMallocHost((void**)&p->h_geom, p->wh * sizeof(float)));
+        p->h_alloc = p->wh;
+    }
+    return MPMVS_OK;
+}
+
+// common tail of the three set_views flavours: cameras, depth range, per-view constants, state buffers
+int finish_views(mpmvs_problem* p, int n, const mpmvs_camera* cams) {
+    p->n = n;
+    memcpy(p->cams, cams, sizeof(mpmvs_camera) * n);
+    p->W = cams[0].width; p->H = cams[0].height;
+    p->wh = (size_t)p->W * p->H;
+    p->depth_min = cams[0].depth_min * 0.6f;   // PatchMatch.cpp:929-930
+    p->depth_max = cams[0].depth_max * 1.2f;
+    for (int v = 1; v < n; ++v) {
+        pm_build_view_consts(cams[0], cams[v], p->hviews[v - 1]);
+        p->hviews[v - 1].layer = p->layers[v];
+    }
+    p->has_depths = false;
+    p->has_prior = false;
+    p->ran = false;
+    int rc = alloc_state(p);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(p->dviews, p->hviews, sizeof(PmView) * (n - 1), cudaMemcpyHostToDevice, p->stream));
+    return MPMVS_OK;
+}
+
+int check_views_args(mpmvs_problem* p, int n, const void* a, const mpmvs_camera* cams) {
+    if (!p || !a || !cams || n < 2 || n > MPMVS_MAX_VIEWS) return MPMVS_E_ARG;
+    for (int i = 0; i < n; ++i)
+        if (cams[i].width <= 0 || cams[i].height <= 0) return MPMVS_E_ARG;
+    return MPMVS_OK;
+}
+
+int private_cache(mpmvs_problem* p, int n, const mpmvs_camera* cams) {
+    int mw = 0, mh = 0;
+    for (int i = 0; i < n; ++i) { mw = cams[i].width > mw ? cams[i].width : mw; mh = cams[i].height > mh ? cams[i].height : mh; }
+    if (p->cache && !p->own_cache) p->cache = nullptr;
+    if (p->cache && (p->cache->W != mw || p->cache->H != mh || p->cache->capacity < n)) {
+        cache_free(p->cache);
+        delete p->cache;
+        p->cache = nullptr;
+    }
+    if (!p->cache) {
+        p->cache = new (std::nothrow) mpmvs_image_cache();
+        if (!p->cache) return MPMVS_E_ARG;
+        p->cache->device = p->device;
+        p->own_cache = true;
+        int rc = cache_alloc(p->cache, mw, mh, n);
+        if (rc) return rc;
+    }
+    for (int i = 0; i < n; ++i) p->layers[i] = i;
+    return MPMVS_OK;
+}
+
+int sync_frame_views(mpmvs_problem* p) {
+    // depth pointers may have changed since finish_views
+    CK(cudaMemcpyAsync(p->dviews, p->hviews, sizeof(PmView) * (p->n - 1), cudaMemcpyHostToDevice, p->stream));
+    return MPMVS_OK;
+}
+
+// PatchMatchCUDA::Run's schedule, PatchMatch.cu:1198-1244
+int enqueue_run(mpmvs_problem* p, uint64_t seed) {
+    if (!p || p->n < 2) return MPMVS_E_ARG;
+    if (p->geom && !p->has_depths) return MPMVS_E_STATE;
+    if (p->planar && !p->has_prior) return MPMVS_E_STATE;
+    CK(cudaSetDevice(p->device));
+    const PmFrame F = make_frame(p);
+    PmState S = p->S;
+    S.counters = nullptr;
+    if (p->profiling & 2) {
+        if (!p->d_counters) CK(cudaMalloc((void**)&p->d_counters, 2 * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(p->d_counters, 0, 2 * sizeof(unsigned long long), p->stream));
+        S.counters = p->d_counters;
+    }
+    p->pev_used = 0;
+    auto mark = [&]() -> cudaError_t {
+        if (!(p->profiling & 1)) return cudaSuccess;
+        if ((size_t)p->pev_used >= p->pev.size()) {
+            cudaEvent_t e;
+            cudaError_t rc = cudaEventCreate(&e);
+            if (rc != cudaSuccess) return rc;
+            p->pev.push_back(e);
+        }
+        return cudaEventRecord(p->pev[p->pev_used++], p->stream);
+    };
+    CK(cudaEventRecord(p->ev0, p->stream));
+    CK(mark());
+    int launches = 0;
+    CK(pm_launch_init(F, S, p->dviews, seed, p->stream));
+    CK(mark());
+    ++launches;
+    if (p->geom || p->planar) {
+        for (int i = 0; i < p->max_iterations; ++i)
+            for (int red = 0; red < 2; ++red) {
+                CK(pm_launch_sweep(F, S, p->dviews, red, i, 0, p->stream));
+                CK(mark());
+                ++launches;
+            }
+    } else {
+        for (int s = p->max_scale; s >= 0; --s)
+            for (int i = 0; i < p->max_iterations; ++i)
+                for (int red = 0; red < 2; ++red) {
+                    CK(pm_launch_sweep(F, S, p->dviews, red, i, s, p->stream));
+                    CK(mark());
+                    ++launches;
+                }
+    }
+    CK(pm_launch_finalize(F, S, p->stream));
+    CK(mark());
+    launches += 3;
+    CK(cudaEventRecord(p->ev1, p->stream));
+    p->last_launches = launches;
+    p->ran = true;
+    return MPMVS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mpmvs_version(void) { return 100; }
+
+const char* mpmvs_error_string(int code) {
+    switch (code) {
+        case MPMVS_OK: return "ok";
+        case MPMVS_E_ARG: return "invalid argument or call order";
+        case MPMVS_E_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+        case MPMVS_E_STATE: return "required input missing for the selected mode";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+    }
+}
+
+int mpmvs_create(int device, void* stream, mpmvs_problem** out) {
+    if (!out) return MPMVS_E_ARG;
+    int rc = ensure_device(device);
+    if (rc) return rc;
+    mpmvs_problem* p = new (std::nothrow) mpmvs_problem();
+    if (!p) return MPMVS_E_ARG;
+    p->device = device;
+    memset(p->d_depths, 0, sizeof(p->d_depths));
+    memset(p->d_depths_cap, 0, sizeof(p->d_depths_cap));
+    if (stream) {
+        p->stream = (cudaStream_t)stream;
+    } else {
+        cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete p; return (int)e; }
+        p->own_stream = true;
+    }
+    cudaEventCreate(&p->ev0);
+    cudaEventCreate(&p->ev1);
+    *out = p;
+    return MPMVS_OK;
+}
+
+int mpmvs_destroy(mpmvs_problem* p) {
+    if (!p) return MPMVS_E_ARG;
+    cudaSetDevice(p->device);
+    cudaStreamSynchronize(p->stream);
+    cudaFree(p->S.planes); cudaFree(p->S.costs); cudaFree(p->S.views); cudaFree(p->S.rng); cudaFree(p->S.geom);
+    cudaFree(p->d_prior); cudaFree(p->d_mask); cudaFree(p->dviews);
+    for (int i = 0; i < PM_MAX_SRC; ++i) cudaFree(p->d_depths[i]);
+    cudaFreeHost(p->h_planes); cudaFreeHost(p->h_costs); cudaFreeHost(p->h_geom);
+    if (p->own_cache && p->cache) { cache_free(p->cache); delete p->cache; }
+    cudaEventDestroy(p->ev0);
+    cudaEventDestroy(p->ev1);
+    for (cudaEvent_t e : p->pev) cudaEventDestroy(e);
+    cudaFree(p->d_counters);
+    if (p->own_stream) cudaStreamDestroy(p->stream);
+    delete p;
+    return MPMVS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- image cache
+int mpmvs_cache_create(int device, int max_width, int max_height, int capacity, mpmvs_image_cache** out) {
+    if (!out || max_width <= 0 || max_height <= 0 || capacity <= 0 || capacity > 2048) return MPMVS_E_ARG;
+    int rc = ensure_device(device);
+    if (rc) return rc;
+    mpmvs_image_cache* c = new (std::nothrow) mpmvs_image_cache();
+    if (!c) return MPMVS_E_ARG;
+    c->device = device;
+    rc = cache_alloc(c, max_width, max_height, capacity);
+    if (rc) { delete c; return rc; }
+    *out = c;
+    return MPMVS_OK;
+}
+
+int mpmvs_cache_destroy(mpmvs_image_cache* c) {
+    if (!c) return MPMVS_E_ARG;
+    cudaSetDevice(c->device);
+    cache_free(c);
+    delete c;
+    return MPMVS_OK;
+}
+
+static int cache_layer_for(mpmvs_image_cache* c, int image_id, int w, int h) {
+    if (w > c->W || h > c->H) return -1;
+    auto it = c->id2layer.find(image_id);
+    if (it != c->id2layer.end()) return it->second;
+    if (c->used >= c->capacity) return -1;
+    const int layer = c->used++;
+    c->id2layer[image_id] = layer;
+    return layer;
+}
+
+int mpmvs_cache_put(mpmvs_image_cache* c, int image_id, const float* gray_host, int width, int height) {
+    if (!c || !gray_host) return MPMVS_E_ARG;
+    CK(cudaSetDevice(c->device));
+    const int layer = cache_layer_for(c, image_id, width, height);
+    if (layer < 0) return MPMVS_E_ARG;
+    int rc = cache_upload(c, layer, gray_host, (size_t)width * sizeof(float), width, height, cudaMemcpyHostToDevice, 0);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(0));
+    return MPMVS_OK;
+}
+
+int mpmvs_cache_put_u8(mpmvs_image_cache* c, int image_id, const uint8_t* gray_host, int width, int height) {
+    if (!c || !gray_host) return MPMVS_E_ARG;
+    // uint8 -> float32 exactly as PatchMatchInit's convertTo(CV_32FC1) (PatchMatch.cpp:882)
+    std::vector<float> tmp((size_t)width * height);
+    for (size_t i = 0; i < tmp.size(); ++i) tmp[i] = (float)gray_host[i];
+    return mpmvs_cache_put(c, image_id, tmp.data(), width, height);
+}
+
+int mpmvs_cache_has(mpmvs_image_cache* c, int image_id) { return c && c->id2layer.count(image_id) ? 1 : 0; }
+
+// ---------------------------------------------------------------------------------------------- inputs
+int mpmvs_set_views(mpmvs_problem* p, int n, const float* const* gray_host, const mpmvs_camera* cams) {
+    int rc = check_views_args(p, n, gray_host, cams);
+    if (rc) return rc;
+    CK(cudaSetDevice(p->device));
+    rc = private_cache(p, n, cams);
+    if (rc) return rc;
+    for (int i = 0; i < n; ++i) {
+        rc = cache_upload(p->cache, i, gray_host[i], (size_t)cams[i].width * sizeof(float), cams[i].width, cams[i].height,
+                          cudaMemcpyHostToDevice, p->stream);
+        if (rc) return rc;
+    }
+    return finish_views(p, n, cams);
+}
+
+int mpmvs_set_views_device(mpmvs_problem* p, int n, const float* const* gray_dev, const size_t* pitch_bytes,
+                           const mpmvs_camera* cams) {
+    int rc = check_views_args(p, n, gray_dev, cams);
+    if (rc) return rc;
+    CK(cudaSetDevice(p->device));
+    rc = private_cache(p, n, cams);
+    if (rc) return rc;
+    for (int i = 0; i < n; ++i) {
+        const size_t pitch = pitch_bytes ? pitch_bytes[i] : (size_t)cams[i].width * sizeof(float);
+        rc = cache_upload(p->cache, i, gray_dev[i], pitch, cams[i].width, cams[i].height, cudaMemcpyDeviceToDevice, p->stream);
+        if (rc) return rc;
+    }
+    return finish_views(p, n, cams);
+}
+
+int mpmvs_set_views_cached(mpmvs_problem* p, mpmvs_image_cache* c, int n, const int* image_ids, const mpmvs_camera* cams) {
+    int rc = check_views_args(p, n, image_ids, cams);
+    if (rc) return rc;
+    if (!c || c->device != p->device) return MPMVS_E_ARG;
+    CK(cudaSetDevice(p->device));
+    if (p->own_cache && p->cache) { cache_free(p->cache); delete p->cache; }
+    p->cache = c;
+    p->own_cache = false;
+    for (int i = 0; i < n; ++i) {
+        auto it = c->id2layer.find(image_ids[i]);
+        if (it == c->id2layer.end()) return MPMVS_E_STATE;
+        if (c->lw[it->second] != cams[i].width || c->lh[it->second] != cams[i].height) return MPMVS_E_ARG;
+        p->layers[i] = it->second;
+    }
+    return finish_views(p, n, cams);
+}
+
+int mpmvs_set_geom_consistency_params(mpmvs_problem* p, int geom_consistency, int planar_prior) {
+    if (!p) return MPMVS_E_ARG;
+    p->geom = geom_consistency != 0;   // PatchMatch.cpp:655-665
+    if (geom_consistency) {
+        p->max_iterations = 2;
+        p->geomPlanarPrior = planar_prior != 0;
+    } else {
+        p->max_iterations = 3;
+    }
+    return MPMVS_OK;
+}
+
+int mpmvs_reset_params(mpmvs_problem* p) {
+    if (!p) return MPMVS_E_ARG;
+    p->max_iterations = 3; p->geom = false; p->geomPlanarPrior = false; p->planar = false;  // PatchMatch.h:48-67 defaults
+    p->has_prior = false;
+    return MPMVS_OK;
+}
+
+int mpmvs_set_planar_prior_params(mpmvs_problem* p) {
+    if (!p) return MPMVS_E_ARG;
+    p->planar = true;                  // PatchMatch.cpp:667-670
+    return MPMVS_OK;
+}
+
+int mpmvs_set_src_depths(mpmvs_problem* p, const float* const* depth_host) {
+    if (!p || !depth_host || p->n < 2) return MPMVS_E_ARG;
+    CK(cudaSetDevice(p->device));
+    for (int v = 0; v < p->n - 1; ++v) {
+        const mpmvs_camera& sc = p->cams[v + 1];
+        const size_t bytes = (size_t)sc.width * sc.height * sizeof(float);
+        if (bytes > p->d_depths_cap[v]) {
+            cudaFree(p->d_depths[v]);
+            p->d_depths[v] = nullptr; p->d_depths_cap[v] = 0;
+            CK(cudaMalloc((void**)&p->d_depths[v], bytes));
+            p->d_depths_cap[v] = bytes;
+        }
+        CK(cudaMemcpyAsync(p->d_depths[v], depth_host[v], bytes, cudaMemcpyHostToDevice, p->stream));
+        p->hviews[v].depth = p->d_depths[v];
+        p->hviews[v].dw = sc.width; p->hviews[v].dh = sc.height; p->hviews[v].dpitch = sc.width;
+    }
+    p->has_depths = true;
+    return sync_frame_views(p);
+}
+
+int mpmvs_set_src_depths_device(mpmvs_problem* p, const float* const* depth_dev, const size_t* pitch_bytes) {
+    if (!p || !depth_dev || p->n < 2) return MPMVS_E_ARG;
+    CK(cudaSetDevice(p->device));
+    for (int v = 0; v < p->n - 1; ++v) {
+        const mpmvs_camera& sc = p->cams[v + 1];
+        p->hviews[v].depth = depth_dev[v];   // used in place: e.g. a slot of the all-gathered depth buffer
+        p->hviews[v].dw = sc.width; p->hviews[v].dh = sc.height;
+        p->hviews[v].dpitch = pitch_bytes ? (int)(pitch_bytes[v] / sizeof(float)) : sc.width;
+    }
+    p->has_depths = true;
+    return sync_frame_views(p);
+}
+
+int mpmvs_set_state(mpmvs_problem* p, const float* planes4_host, const float* costs_host) {
+    if (!p || !planes4_host || !costs_host || p->n < 2) return MPMVS_E_ARG;
+    CK(cudaSetDevice(p->device));
+    CK(cudaMemcpyAsync(p->S.planes, planes4_host, p->wh * sizeof(pm_f4), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(p->S.costs, costs_host, p->wh * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaStreamSynchronize(p->stream));  // the caller may free its buffers on return
+    return MPMVS_OK;
+}
+
+int mpmvs_set_prior(mpmvs_problem* p, const float* prior_planes4_host, const uint32_t* mask_host) {
+    if (!p || !prior_planes4_host || !mask_host || p->n < 2) return MPMVS_E_ARG;
+    CK(cudaSetDevice(p->device));
+    CK(cudaMemcpyAsync(p->d_prior, prior_planes4_host, p->wh * sizeof(pm_f4), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(p->d_mask, mask_host, p->wh * sizeof(uint32_t), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    p->has_prior = true;
+    return MPMVS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- run
+int mpmvs_run_async(mpmvs_problem* p, uint64_t seed) { return enqueue_run(p, seed); }
+
+int mpmvs_synchronize(mpmvs_problem* p) {
+    if (!p) return MPMVS_E_ARG;
+    CK(cudaStreamSynchronize(p->stream));
+    return MPMVS_OK;
+}
+
+int mpmvs_run_into(mpmvs_problem* p, uint64_t seed, float* planes4_host, float* costs_host, float* geom_costs_host) {
+    int rc = enqueue_run(p, seed);
+    if (rc) return rc;
+    // PatchMatch.cu:1246-1251
+    if (planes4_host) CK(cudaMemcpyAsync(planes4_host, p->S.planes, p->wh * sizeof(pm_f4), cudaMemcpyDeviceToHost, p->stream));
+    if (costs_host) CK(cudaMemcpyAsync(costs_host, p->S.costs, p->wh * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    if (geom_costs_host) CK(cudaMemcpyAsync(geom_costs_host, p->S.geom, p->wh * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return MPMVS_OK;
+}
+
+int mpmvs_run(mpmvs_problem* p, uint64_t seed) {
+    if (!p) return MPMVS_E_ARG;
+    int rc = ensure_mirrors(p);
+    if (rc) return rc;
+    return mpmvs_run_into(p, seed, p->h_planes, p->h_costs, p->geomPlanarPrior ? p->h_geom : nullptr);
+}
+
+int mpmvs_last_run_ms(mpmvs_problem* p, float* ms) {
+    if (!p || !ms || !p->ran) return MPMVS_E_ARG;
+    CK(cudaEventSynchronize(p->ev1));
+    CK(cudaEventElapsedTime(ms, p->ev0, p->ev1));
+    return MPMVS_OK;
+}
+
+int mpmvs_set_profiling(mpmvs_problem* p, int flags) {
+    if (!p) return MPMVS_E_ARG;
+    p->profiling = flags;
+    return MPMVS_OK;
+}
+
+int mpmvs_last_run_profile(mpmvs_problem* p, float* init_ms, float* sweep_ms, int* n_sweeps, float* finalize_ms,
+                           uint64_t* ncc_evaluations) {
+    if (!p || !p->ran) return MPMVS_E_ARG;
+    CK(cudaSetDevice(p->device));
+    CK(cudaEventSynchronize(p->ev1));
+    if (p->profiling & 1) {
+        const int ne = p->pev_used;
+        if (ne < 3) return MPMVS_E_STATE;
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, p->pev[0], p->pev[1]));
+        if (init_ms) *init_ms = ms;
+        CK(cudaEventElapsedTime(&ms, p->pev[1], p->pev[ne - 2]));
+        if (sweep_ms) *sweep_ms = ms;
+        if (n_sweeps) *n_sweeps = ne - 3;
+        CK(cudaEventElapsedTime(&ms, p->pev[ne - 2], p->pev[ne - 1]));
+        if (finalize_ms) *finalize_ms = ms;
+    } else if (init_ms || sweep_ms || finalize_ms) {
+        return MPMVS_E_STATE;
+    }
+    if (ncc_evaluations) {
+        if (!(p->profiling & 2) || !p->d_counters) return MPMVS_E_STATE;
+        unsigned long long c[2];
+        CK(cudaMemcpy(c, p->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+        *ncc_evaluations = c[0];
+    }
+    return MPMVS_OK;
+}
+
+int mpmvs_last_run_launches(mpmvs_problem* p, int* launches) {
+    if (!p || !launches) return MPMVS_E_ARG;
+    *launches = p->last_launches;
+    return MPMVS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- results
+int mpmvs_get_size(mpmvs_problem* p, int* width, int* height) {
+    if (!p || p->n < 2) return MPMVS_E_ARG;
+    if (width) *width = p->W;
+    if (height) *height = p->H;
+    return MPMVS_OK;
+}
+
+int mpmvs_get_depth_range(mpmvs_problem* p, float* depth_min, float* depth_max) {
+    if (!p || p->n < 2) return MPMVS_E_ARG;
+    if (depth_min) *depth_min = p->depth_min;
+    if (depth_max) *depth_max = p->depth_max;
+    return MPMVS_OK;
+}
+
+int mpmvs_get_planes(mpmvs_problem* p, float* planes4_host) {
+    if (!p || !planes4_host || !p->h_planes) return MPMVS_E_ARG;
+    memcpy(planes4_host, p->h_planes, p->wh * sizeof(pm_f4));
+    return MPMVS_OK;
+}
+int mpmvs_get_costs(mpmvs_problem* p, float* costs_host) {
+    if (!p || !costs_host || !p->h_costs) return MPMVS_E_ARG;
+    memcpy(costs_host, p->h_costs, p->wh * sizeof(float));
+    return MPMVS_OK;
+}
+int mpmvs_get_geom_costs(mpmvs_problem* p, float* geom_costs_host) {
+    if (!p || !geom_costs_host || p->n < 2) return MPMVS_E_ARG;
+    CK(cudaSetDevice(p->device));
+    CK(cudaMemcpyAsync(geom_costs_host, p->S.geom, p->wh * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return MPMVS_OK;
+}
+
+int mpmvs_device_planes(mpmvs_problem* p, const float** planes4_dev) {
+    if (!p || !planes4_dev || p->n < 2) return MPMVS_E_ARG;
+    *planes4_dev = (const float*)p->S.planes;
+    return MPMVS_OK;
+}
+int mpmvs_device_costs(mpmvs_problem* p, const float** costs_dev) {
+    if (!p || !costs_dev || p->n < 2) return MPMVS_E_ARG;
+    *costs_dev = p->S.costs;
+    return MPMVS_OK;
+}
+int mpmvs_export_depth_device(mpmvs_problem* p, float* depth_dev, size_t pitch_bytes) {
+    if (!p || !depth_dev || p->n < 2) return MPMVS_E_ARG;
+    CK(cudaSetDevice(p->device));
+    const int pitch_f = pitch_bytes ? (int)(pitch_bytes / sizeof(float)) : p->W;
+    CK(pm_launch_export_depth(p->S.planes, depth_dev, p->W, p->H, pitch_f, p->stream));
+    return MPMVS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- stage hooks
+int mpmvs_init_only(mpmvs_problem* p, uint64_t seed) {
+    if (!p || p->n < 2) return MPMVS_E_ARG;
+    CK(cudaSetDevice(p->device));
+    CK(pm_launch_init(make_frame(p), p->S, p->dviews, seed, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return MPMVS_OK;
+}
+
+int mpmvs_half_sweep(mpmvs_problem* p, int red, int iter, int scale) {
+    if (!p || p->n < 2) return MPMVS_E_ARG;
+    if (p->geom && !p->has_depths) return MPMVS_E_STATE;
+    CK(cudaSetDevice(p->device));
+    CK(pm_launch_sweep(make_frame(p), p->S, p->dviews, red ? 1 : 0, iter, scale, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return MPMVS_OK;
+}
+
+int mpmvs_finalize(mpmvs_problem* p) {
+    if (!p || p->n < 2) return MPMVS_E_ARG;
+    CK(cudaSetDevice(p->device));
+    CK(pm_launch_finalize(make_frame(p), p->S, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return MPMVS_OK;
+}
+
+int mpmvs_get_device_state(mpmvs_problem* p, float* planes4, float* costs, uint32_t* views, uint32_t* rng6, float* geom) {
+    if (!p || p->n < 2) return MPMVS_E_ARG;
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->stream));
+    if (planes4) CK(cudaMemcpy(planes4, p->S.planes, p->wh * sizeof(pm_f4), cudaMemcpyDeviceToHost));
+    if (costs) CK(cudaMemcpy(costs, p->S.costs, p->wh * sizeof(float), cudaMemcpyDeviceToHost));
+    if (views) CK(cudaMemcpy(views, p->S.views, p->wh * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (rng6) CK(cudaMemcpy(rng6, p->S.rng, p->wh * 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (geom) CK(cudaMemcpy(geom, p->S.geom, p->wh * sizeof(float), cudaMemcpyDeviceToHost));
+    return MPMVS_OK;
+}
+
+int mpmvs_set_device_state(mpmvs_problem* p, const float* planes4, const float* costs, const uint32_t* views,
+                           const uint32_t* rng6, const float* geom) {
+    if (!p || p->n < 2) return MPMVS_E_ARG;
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->stream));
+    if (planes4) CK(cudaMemcpy(p->S.planes, planes4, p->wh * sizeof(pm_f4), cudaMemcpyHostToDevice));
+    if (costs) CK(cudaMemcpy(p->S.costs, costs, p->wh * sizeof(float), cudaMemcpyHostToDevice));
+    if (views) CK(cudaMemcpy(p->S.views, views, p->wh * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (rng6) CK(cudaMemcpy(p->S.rng, rng6, p->wh * 6 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (geom) CK(cudaMemcpy(p->S.geom, geom, p->wh * sizeof(float), cudaMemcpyHostToDevice));
+    return MPMVS_OK;
+}
+
+int mpmvs_ncc_map(mpmvs_problem* p, const float* planes4_host, int scale, float* out_host) {
+    if (!p || !planes4_host || !out_host || p->n < 2 || scale < 0 || scale > 2) return MPMVS_E_ARG;
+    CK(cudaSetDevice(p->device));
+    pm_f4* dp = nullptr;
+    float* dout = nullptr;
+    const size_t out_bytes = p->wh * (p->n - 1) * sizeof(float);
+    CK(cudaMalloc((void**)&dp, p->wh * sizeof(pm_f4)));
+    cudaError_t e = cudaMalloc((void**)&dout, out_bytes);
+    if (e != cudaSuccess) { cudaFree(dp); return (int)e; }
+    cudaMemcpyAsync(dp, planes4_host, p->wh * sizeof(pm_f4), cudaMemcpyHostToDevice, p->stream);
+    e = pm_launch_ncc_map(make_frame(p), p->dviews, dp, scale, dout, p->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, dout, out_bytes, cudaMemcpyDeviceToHost, p->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+    cudaFree(dp);
+    cudaFree(dout);
+    return (int)e;
+}
+
+int mpmvs_geom_map(mpmvs_problem* p, const float* planes4_host, float* out_host) {
+    if (!p || !planes4_host || !out_host || p->n < 2) return MPMVS_E_ARG;
+    if (!p->has_depths) return MPMVS_E_STATE;
+    CK(cudaSetDevice(p->device));
+    pm_f4* dp = nullptr;
+    float* dout = nullptr;
+    const size_t out_bytes = p->wh * (p->n - 1) * sizeof(float);
+    CK(cudaMalloc((void**)&dp, p->wh * sizeof(pm_f4)));
+    cudaError_t e = cudaMalloc((void**)&dout, out_bytes);
+    if (e != cudaSuccess) { cudaFree(dp); return (int)e; }
+    cudaMemcpyAsync(dp, planes4_host, p->wh * sizeof(pm_f4), cudaMemcpyHostToDevice, p->stream);
+    e = pm_launch_geom_map(make_frame(p), p->dviews, dp, dout, p->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, dout, out_bytes, cudaMemcpyDeviceToHost, p->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+    cudaFree(dp);
+    cudaFree(dout);
+    return (int)e;
+}
+
+int mpmvs_uniform_stream(uint64_t seed, int x, int y, int n, float* out_host) {
+    if (!out_host || n <= 0) return MPMVS_E_ARG;
+    int rc = ensure_device(0);
+    if (rc) return rc;
+    float* d = nullptr;
+    CK(cudaMalloc((void**)&d, sizeof(float) * n));
+    cudaError_t e = pm_launch_uniform_stream(seed, x, y, n, d, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(out_host, d, sizeof(float) * n, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return (int)e;
+}
+
+}  // extern "C"

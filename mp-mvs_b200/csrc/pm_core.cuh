@@ -1,0 +1,720 @@
+// pm_core.cuh -- per-pixel arithmetic of the PatchMatch path, written once for the sm_100a kernels.
+//
+// Behavioural spec: /root/reference/src/PatchMatch.cu ("cu:NNN" below). This is not a transcription:
+//   * the homography is evaluated in the hoisted form H = A_v + b_v m^T (per-view constants A_v, b_v
+//     prepared on the host; m = K_r^-T n / d per hypothesis), so a warped tap costs 5 FMA + 1 RCP instead
+//     of a 145-flop rebuild per NCC call (cu:228-288);
+//   * everything that depends only on (pixel, scale) -- bilateral weights' reference side, the weighted
+//     reference mean/variance -- is computed once per pixel per sweep, not once per (hypothesis, view);
+//   * the reference window comes from a shared-memory tile (Ctx::ref), source samples from the texture
+//     unit (Ctx::src), source depths from plain global loads (Ctx::src_depth);
+//   * views with zero sampling weight are skipped where the reference multiplies their cost by 0
+//     (cu:684-694, 904-913): result-identical, costs are always finite;
+//   * per-pixel scratch that the reference keeps in 1.5 KB of local arrays is reduced to the 8 x nsrc
+//     candidate cost table; view weights are 4-bit counters packed in two 64-bit registers.
+// All reference quirks that change results are kept and marked QUIRK.
+//
+// The functions are templates over a context `Ctx` so that the very same code can be instantiated by
+// the test-only host emulation (tests/emul), which is how the logic is debugged without a GPU. The
+// product library only ever instantiates the device context in pm_kernels.cu.
+#ifndef MPMVS_PM_CORE_CUH
+#define MPMVS_PM_CORE_CUH
+
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PM_HD __host__ __device__ __forceinline__
+#define PM_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define PM_HD inline
+#define PM_HD_NOINLINE
+#endif
+
+#define PM_MAX_SRC 32
+#define PM_PI_F 3.14159265358979323846f
+
+struct alignas(16) pm_f4 { float x, y, z, w; };
+
+// Per-source-view constants, prepared on the host in double precision (pm_capi.cu: build_view_consts).
+struct PmView {
+    float A[9];   // K_s R_rel K_r^-1        (homography, cu:228-279 with n/d factored out)
+    float b[3];   // -K_s t_rel
+    float w, h;   // source image size as float (bounds test of the warped centre, cu:351)
+    float Mf[9];  // K_s R_s R_r^T K_r^-1     ref pixel (x,y,1)*z -> source homogeneous pixel (cu:582-615)
+    float vf[3];  // K_s (R_s C_r + t_s)
+    float Mb[9];  // K_r R_r R_s^T K_s^-1     source pixel*z_s -> reference homogeneous pixel
+    float vb[3];  // K_r (R_r C_s + t_r)
+    int dw, dh;   // source depth-map size
+    int dpitch;   // in floats
+    int layer;    // layer of this view in the resident layered image texture
+    const float* depth;        // source depth map (geom pass), linear device memory
+};
+
+// Reference-camera constants and run flags.
+struct PmFrame {
+    float fx, fy, cx, cy;      // K[0], K[4], K[2], K[5] of the reference view
+    float ifx, ify;            // 1/fx, 1/fy
+    float fx_over_fy;          // K[0]/K[4] (cu:86)
+    float R[9];                // reference rotation (cu:89-97, 308-316)
+    float depth_min, depth_max;
+    float spat_k;              // -log2(e) / (2 sigma_spatial^2)
+    float col_k;               //  log2(e) / (2 sigma_color^2)
+    int W, H, nsrc, top_k;
+    int geom, planar;
+    int ref_layer;             // layer of the reference image
+    int soft_clamp;            // 1 when the views differ in size: clamp-to-edge is then done on the coordinates
+    unsigned long long tex;    // cudaTextureObject_t of the layered image array (one handle, warp-uniform:
+                               // a per-view handle makes the compiler serialise every fetch per unique handle)
+};
+
+// Device-resident per-pixel state (SoA).
+struct PmState {
+    pm_f4* planes;             // (n, d) camera frame while sweeping; (world n, depth) after finalize
+    float* costs;
+    uint32_t* views;           // selected-view bit mask
+    uint32_t* rng;             // 6 words per pixel: d, v0..v4 (XORWOW)
+    float* geom;
+    const pm_f4* prior;
+    const uint32_t* mask;
+    unsigned long long* counters;  // optional (profiling): [0] += NCC evaluations that ran their 36 taps
+};
+
+// ------------------------------------------------------------------------------------------------ math
+PM_HD float pm_ex2(float x) { return exp2f(x); }
+#if defined(__CUDA_ARCH__)
+PM_HD float pm_exp(float x) { return __expf(x); }
+PM_HD float pm_rsqrt(float x) { return rsqrtf(x); }
+PM_HD int pm_ffs(uint32_t m) { return __ffs((int)m); }
+PM_HD int pm_f2i(float f) { return __float2int_rz(f); }  // saturating, NaN -> 0 (what `(int)` compiles to)
+#else
+PM_HD float pm_exp(float x) { return expf(x); }
+PM_HD float pm_rsqrt(float x) { return 1.0f / sqrtf(x); }
+PM_HD int pm_ffs(uint32_t m) { return __builtin_ffs((int)m); }
+PM_HD int pm_f2i(float f) {
+    if (f != f) return 0;
+    if (f >= 2147483648.0f) return 2147483647;
+    if (f <= -2147483648.0f) return (-2147483647 - 1);
+    return (int)f;
+}
+#endif
+
+PM_HD void pm_count(unsigned long long* ctr, uint32_t n) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(ctr, (unsigned long long)n);
+#else
+    *ctr += n;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------ RNG
+// XORWOW with cuRAND's start state for curand_init(seed, 0, 0) and curand_uniform's output map, so a
+// pixel draws the same stream as the fixed-seed reference build (oracle/ref_harness.cu).
+struct PmRng { uint32_t d, v0, v1, v2, v3, v4; };
+
+PM_HD uint64_t pm_mix_seed(uint64_t seed, uint32_t x, uint32_t y) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ULL * ((((uint64_t)y) << 32) | (uint64_t)x) + 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+PM_HD void pm_rng_init(PmRng& s, uint64_t seed) {
+    const uint32_t s0 = ((uint32_t)seed) ^ 0xaad26b49u, s1 = (uint32_t)(seed >> 32) ^ 0xf7dcefddu;
+    const uint32_t t0 = 1099087573u * s0, t1 = 2591861531u * s1;
+    s.d = 6615241u + t1 + t0;
+    s.v0 = 123456789u + t0; s.v1 = 362436069u ^ t0; s.v2 = 521288629u + t1; s.v3 = 88675123u ^ t1; s.v4 = 5783321u + t0;
+}
+PM_HD float pm_uniform(PmRng& s) {  // (0, 1]
+    const uint32_t t = s.v0 ^ (s.v0 >> 2);
+    s.v0 = s.v1; s.v1 = s.v2; s.v2 = s.v3; s.v3 = s.v4;
+    s.v4 = (s.v4 ^ (s.v4 << 4)) ^ (t ^ (t << 1));
+    s.d += 362437u;
+    return fmaf((float)(s.v4 + s.d), 2.3283064e-10f, 2.3283064e-10f / 2.0f);
+}
+PM_HD PmRng pm_rng_load(const uint32_t* g, int idx) {
+    const uint32_t* p = g + 6 * (size_t)idx;
+    PmRng s; s.d = p[0]; s.v0 = p[1]; s.v1 = p[2]; s.v2 = p[3]; s.v3 = p[4]; s.v4 = p[5];
+    return s;
+}
+PM_HD void pm_rng_store(uint32_t* g, int idx, const PmRng& s) {
+    uint32_t* p = g + 6 * (size_t)idx;
+    p[0] = s.d; p[1] = s.v0; p[2] = s.v1; p[3] = s.v2; p[4] = s.v3; p[5] = s.v4;
+}
+
+// ------------------------------------------------------------------------------------------------ geometry
+PM_HD float pm_dot3(const pm_f4& a, const pm_f4& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+// ComputeDepthfromPlaneHypothesis, cu:84-87
+PM_HD float pm_depth_from_plane(const PmFrame& F, const pm_f4& pl, int x, int y) {
+    return -pl.w * F.fx / ((x - F.cx) * pl.x + F.fx_over_fy * (y - F.cy) * pl.y + F.fx * pl.z);
+}
+// GetPlane2Origin, cu:163-176
+PM_HD float pm_plane_distance(const PmFrame& F, int x, int y, float depth, const pm_f4& n) {
+    const float X0 = depth * (x - F.cx) / F.fx, X1 = depth * (y - F.cy) / F.fy;
+    return -(n.x * X0 + n.y * X1 + n.z * depth);
+}
+PM_HD void pm_normalize(pm_f4& v) {  // cu:188-195
+    const float inv = pm_rsqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+    v.x *= inv; v.y *= inv; v.z *= inv;
+}
+// GenerateRandomNormal, cu:197-219 (Marsaglia; flipped to face the camera)
+PM_HD pm_f4 pm_random_normal(const PmFrame& F, int x, int y, PmRng& rs) {
+    float q1, q2, s;
+    do {
+        q1 = 2.f * pm_uniform(rs) - 1.f;
+        q2 = 2.f * pm_uniform(rs) - 1.f;
+        s = q1 * q1 + q2 * q2;
+    } while (s >= 1.f);
+    const float sq = sqrtf(1.f - s);
+    pm_f4 n = {2.0f * q1 * sq, 2.0f * q2 * sq, 1.0f - 2.0f * s, 0.f};
+    const float vx = (x - F.cx) / F.fx, vy = (y - F.cy) / F.fy;
+    if (n.x * vx + n.y * vy + n.z > 0.0f) { n.x = -n.x; n.y = -n.y; n.z = -n.z; }
+    pm_normalize(n);
+    return n;
+}
+// GenerateRandomPlaneHypothesis, cu:221-226
+PM_HD pm_f4 pm_random_plane(const PmFrame& F, int x, int y, PmRng& rs) {
+    pm_f4 pl = pm_random_normal(F, x, y, rs);
+    const float depth = pm_uniform(rs) * (F.depth_max - F.depth_min) + F.depth_min;
+    pl.w = pm_plane_distance(F, x, y, depth, pl);
+    return pl;
+}
+// GeneratePerturbedNormal, cu:460-495 (three Euler angles; keeps the old normal if the new one faces away)
+PM_HD pm_f4 pm_perturbed_normal(const PmFrame& F, int x, int y, const pm_f4& normal, PmRng& rs, float perturbation) {
+    const float vx = (x - F.cx) / F.fx, vy = (y - F.cy) / F.fy;
+    const float a1 = (pm_uniform(rs) - 0.5f) * perturbation;
+    const float a2 = (pm_uniform(rs) - 0.5f) * perturbation;
+    const float a3 = (pm_uniform(rs) - 0.5f) * perturbation;
+    const float s1 = sinf(a1), s2 = sinf(a2), s3 = sinf(a3), c1 = cosf(a1), c2 = cosf(a2), c3 = cosf(a3);
+    pm_f4 o;
+    o.x = (c2 * c3) * normal.x + (c3 * s1 * s2 - c1 * s3) * normal.y + (s1 * s3 + c1 * c3 * s2) * normal.z;
+    o.y = (c2 * s3) * normal.x + (c1 * c3 + s1 * s2 * s3) * normal.y + (c1 * s2 * s3 - c3 * s1) * normal.z;
+    o.z = (-s2) * normal.x + (c2 * s1) * normal.y + (c1 * c2) * normal.z;
+    o.w = 0.f;
+    if (o.x * vx + o.y * vy + o.z >= 0.0f) return normal;
+    pm_normalize(o);
+    return o;
+}
+
+// ------------------------------------------------------------------------------------------------ NCC
+// Spatial tap distance |(i,j)| in units of step/2, i,j in {+-1,+-3,+-5}: one of six constants.
+PM_HD constexpr float pm_tap_dist(int u, int v) {
+    return (u * u + v * v == 2)    ? 1.41421356237f
+           : (u * u + v * v == 10) ? 3.16227766017f
+           : (u * u + v * v == 26) ? 5.09901951359f
+           : (u * u + v * v == 18) ? 4.24264068712f
+           : (u * u + v * v == 34) ? 5.83095189485f
+                                   : 7.07106781187f;
+}
+
+// Reference-side statistics of one pixel at one scale: hypothesis-invariant (hoisted out of cu:341-414).
+struct PmRefStats {
+    float r0;        // centre intensity
+    float inv_sw;    // 1 / sum w
+    float mean_r;    // sum w r / sum w
+    float var_r;     // weighted variance of the reference patch
+};
+
+template <int SCALE, class Ctx>
+PM_HD PmRefStats pm_ref_stats(const Ctx& c, const PmFrame& F) {
+    constexpr int HS = 1 << SCALE;  // step/2: taps at (2a-5)*HS
+    PmRefStats st;
+    st.r0 = c.ref(0, 0);
+    float sw = 0.f, swr = 0.f, swrr = 0.f;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+            const int u = 2 * a - 5, v = 2 * b - 5;
+            const float r = c.ref(u * HS, v * HS);
+            const float w = pm_ex2(fmaf(fabsf(r - st.r0), -F.col_k, (HS * pm_tap_dist(u, v)) * F.spat_k));
+            sw += w;
+            swr = fmaf(w, r, swr);
+            swrr = fmaf(w * r, r, swrr);
+        }
+    }
+    st.inv_sw = 1.0f / sw;
+    st.mean_r = swr * st.inv_sw;
+    st.var_r = swrr * st.inv_sw - st.mean_r * st.mean_r;
+    return st;
+}
+
+// Per-hypothesis part of the homography: m = K_r^-T n / d, q0 = m . (x, y, 1)  (= -1/z at the pixel).
+struct PmHyp { float mx, my, q0; };
+PM_HD PmHyp pm_hyp(const PmFrame& F, const pm_f4& pl, int x, int y) {
+    const float id = 1.0f / pl.w;
+    PmHyp h;
+    h.mx = pl.x * F.ifx * id;
+    h.my = pl.y * F.ify * id;
+    const float mz = (pl.z - pl.x * F.cx * F.ifx - pl.y * F.cy * F.ify) * id;
+    h.q0 = fmaf(h.mx, (float)x, fmaf(h.my, (float)y, mz));
+    return h;
+}
+
+// ComputeBilateralNCC, cu:325-414: cost of hypothesis `hyp` at pixel (x,y) against source view v.
+template <int SCALE, class Ctx>
+PM_HD float pm_ncc(const Ctx& c, const PmFrame& F, const PmRefStats& st, int v, const PmHyp& hyp, int x, int y,
+                   uint32_t& nexec) {
+    constexpr int HS = 1 << SCALE;
+    const PmView& V = c.view(v);
+    const float fxp = (float)x, fyp = (float)y;
+    // warped centre  P0 = A (x,y,1) + b q0 ; tap steps  U = H e_x, Vv = H e_y
+    const float X0 = fmaf(V.b[0], hyp.q0, fmaf(V.A[0], fxp, fmaf(V.A[1], fyp, V.A[2])));
+    const float Y0 = fmaf(V.b[1], hyp.q0, fmaf(V.A[3], fxp, fmaf(V.A[4], fyp, V.A[5])));
+    const float Z0 = fmaf(V.b[2], hyp.q0, fmaf(V.A[6], fxp, fmaf(V.A[7], fyp, V.A[8])));
+    const float rz0 = 1.0f / Z0;
+    const float pcx = X0 * rz0, pcy = Y0 * rz0;
+    if (pcx >= V.w || pcx < 0.0f || pcy >= V.h || pcy < 0.0f) return 2.0f;  // cu:351-353
+    if (st.var_r < 1e-5f) return 2.0f;                                     // cu:407 (hypothesis-invariant)
+    ++nexec;
+    const float Ux = fmaf(V.b[0], hyp.mx, V.A[0]), Uy = fmaf(V.b[1], hyp.mx, V.A[3]), Uz = fmaf(V.b[2], hyp.mx, V.A[6]);
+    const float Vx = fmaf(V.b[0], hyp.my, V.A[1]), Vy = fmaf(V.b[1], hyp.my, V.A[4]), Vz = fmaf(V.b[2], hyp.my, V.A[7]);
+    float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        const int i = (2 * a - 5) * HS;
+        const float Xa = fmaf((float)i, Ux, X0), Ya = fmaf((float)i, Uy, Y0), Za = fmaf((float)i, Uz, Z0);
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+            const int j = (2 * b - 5) * HS;
+            const float Z = fmaf((float)j, Vz, Za);
+            const float rz = 1.0f / Z;
+            const float xs = fmaf(fmaf((float)j, Vx, Xa), rz, 0.5f);
+            const float ys = fmaf(fmaf((float)j, Vy, Ya), rz, 0.5f);
+            const float s = c.src(v, xs, ys);
+            const float r = c.ref(i, j);
+            const float w = pm_ex2(fmaf(fabsf(r - st.r0), -F.col_k, (HS * pm_tap_dist(2 * a - 5, 2 * b - 5)) * F.spat_k));
+            const float ws = w * s;
+            s1 += ws;
+            s2 = fmaf(ws, s, s2);
+            s3 = fmaf(ws, r, s3);
+        }
+    }
+    const float mean_s = s1 * st.inv_sw;
+    const float var_s = s2 * st.inv_sw - mean_s * mean_s;
+    if (var_s < 1e-5f) return 2.0f;
+    const float cov = s3 * st.inv_sw - st.mean_r * mean_s;
+    return fmaxf(0.0f, fminf(2.0f, 1.0f - cov * pm_rsqrt(st.var_r * var_s)));
+}
+
+// ComputeGeomConsistencyCost, cu:617-640, with the four camera transforms pre-multiplied per view.
+template <class Ctx>
+PM_HD float pm_geom_cost(const Ctx& c, const PmFrame& F, int v, const pm_f4& pl, int x, int y) {
+    const PmView& V = c.view(v);
+    const float z = pm_depth_from_plane(F, pl, x, y);
+    const float fxp = (float)x, fyp = (float)y;
+    const float hx = fmaf(z, fmaf(V.Mf[0], fxp, fmaf(V.Mf[1], fyp, V.Mf[2])), V.vf[0]);
+    const float hy = fmaf(z, fmaf(V.Mf[3], fxp, fmaf(V.Mf[4], fyp, V.Mf[5])), V.vf[1]);
+    const float hz = fmaf(z, fmaf(V.Mf[6], fxp, fmaf(V.Mf[7], fyp, V.Mf[8])), V.vf[2]);
+    const float sx = hx / hz, sy = hy / hz;
+    const float sd = c.src_depth(v, pm_f2i(sx), pm_f2i(sy));
+    if (sd == 0.0f) return 3.0f;
+    const float bx = fmaf(sd, fmaf(V.Mb[0], sx, fmaf(V.Mb[1], sy, V.Mb[2])), V.vb[0]);
+    const float by = fmaf(sd, fmaf(V.Mb[3], sx, fmaf(V.Mb[4], sy, V.Mb[5])), V.vb[1]);
+    const float bz = fmaf(sd, fmaf(V.Mb[6], sx, fmaf(V.Mb[7], sy, V.Mb[8])), V.vb[2]);
+    const float dc = fxp - bx / bz, dr = fyp - by / bz;
+    return fminf(3.0f, sqrtf(dc * dc + dr * dr));
+}
+
+// ------------------------------------------------------------------------------------------------ view weights
+// Monte-Carlo view weights are integer counts <= 15 (15 samples, cu:856): 4 bits per view, 32 views.
+struct PmWeights {
+    uint64_t lo, hi;
+    PM_HD int get(int v) const { return (int)(((v < 16 ? lo : hi) >> ((v & 15) * 4)) & 15ull); }
+    PM_HD void inc(int v) { if (v < 16) lo += 1ull << (v * 4); else hi += 1ull << ((v - 16) * 4); }
+};
+
+// ComputeMultiViewInitialCostandSelectedViews, cu:497-534: mean of the top_k smallest costs; mask of views <= k-th.
+template <int SCALE, class Ctx>
+PM_HD float pm_initial_cost(const Ctx& c, const PmFrame& F, const PmRefStats& st, const pm_f4& pl, int x, int y,
+                            uint32_t& selected, uint32_t& nexec) {
+    const PmHyp hyp = pm_hyp(F, pl, x, y);
+    float cv[PM_MAX_SRC];
+    int valid = 0;
+    for (int v = 0; v < F.nsrc; ++v) {
+        const float cst = pm_ncc<SCALE>(c, F, st, v, hyp, x, y, nexec);
+        cv[v] = cst;
+        if (cst < 2.0f) ++valid;
+    }
+    selected = 0;
+    const int k = valid < F.top_k ? valid : F.top_k;
+    if (k <= 0) return 2.0f;
+    // k-th smallest by repeated selection (k <= 4): same values as the reference's full insertion sort
+    float sum = 0.f, thr = -1.0f;
+    uint32_t used = 0;
+    for (int t = 0; t < k; ++t) {
+        float best = FLT_MAX; int bi = 0;
+        for (int v = 0; v < F.nsrc; ++v)
+            if (!((used >> v) & 1u) && cv[v] < best) { best = cv[v]; bi = v; }
+        used |= 1u << bi;
+        sum += best;
+        thr = best;
+    }
+    for (int v = 0; v < F.nsrc; ++v) if (cv[v] <= thr) selected |= 1u << v;
+    return sum / k;
+}
+
+// ------------------------------------------------------------------------------------------------ propagation
+// Candidate offsets of the 8 sampling regions, cu:769-779, generated instead of tabulated:
+// regions 0-3 are V-shaped (12 samples), regions 4-7 axial rays at odd distances 5..23 (10 samples).
+PM_HD void pm_region_offset(int r, int k, int& dx, int& dy) {
+    if (r < 4) {
+        const int t = k >> 1, sgn = (k & 1) ? 1 : -1;   // pairs (-a, ..), (+a, ..)
+        const int a = 5 + t, b = 6 + t;
+        if (r == 0) { dx = sgn * a; dy = -b; }
+        else if (r == 1) { dx = sgn * a; dy = b; }
+        else if (r == 2) { dx = -b; dy = sgn * a; }
+        else { dx = b; dy = sgn * a; }
+    } else {
+        const int d = 5 + 2 * k;
+        if (r == 4) { dx = 0; dy = -d; }
+        else if (r == 5) { dx = 0; dy = d; }
+        else if (r == 6) { dx = -d; dy = 0; }
+        else { dx = d; dy = 0; }
+    }
+}
+
+// One pixel of one checkerboard half-sweep: CheckerboardPropagation (cu:724-998) with
+// PlaneHypothesisRefinement (cu:642-722) folded in.
+//
+// The 14 hypotheses a pixel evaluates per half-sweep -- 8 propagation candidates, its current plane,
+// 5 refinement proposals -- run through ONE loop with ONE inlined copy of the 36-tap NCC, so the hot
+// code stays small enough for the instruction cache; the decisions the reference takes between those
+// evaluations (view selection, candidate choice, proposal generation) sit at the top of iterations 8 and 9.
+// `ca` is the thread's private candidate cost table, 8 x nsrc floats (cost_array, cu:795).
+template <int SCALE, class Ctx>
+PM_HD void pm_sweep_pixel(const Ctx& c, const PmFrame& F, const PmState& S, int x, int y, int iter, float* ca) {
+    const int W = F.W, H = F.H, nsrc = F.nsrc;
+    const int idx = y * W + x;
+    PmRng rs = pm_rng_load(S.rng, idx);
+    const PmRefStats st = pm_ref_stats<SCALE>(c, F);
+    uint32_t nexec = 0;
+    const uint32_t all_views = nsrc >= 32 ? 0xffffffffu : ((1u << nsrc) - 1u);
+
+    // ---- best-cost sample of each region (cu:798-816)
+    int pos[8];
+    uint32_t flags = 0;
+#pragma unroll 1
+    for (int r = 0; r < 8; ++r) {
+        const int nk = r < 4 ? 12 : 10;
+        float best = FLT_MAX; int bpos = -1;
+        for (int k = 0; k < nk; ++k) {
+            int dx, dy;
+            pm_region_offset(r, k, dx, dy);
+            const int nx = x + dx, ny = y + dy;
+            if (!(nx >= 0 && ny >= 0 && nx < W && ny < H)) continue;
+            const float nc = S.costs[ny * W + nx];
+            if (best > nc) { best = nc; bpos = ny * W + nx; }
+        }
+        pos[r] = bpos;
+        if (best < FLT_MAX) flags |= 1u << r;
+    }
+    // QUIRK cu:795: `float cost_array[8][32] = {2.0f}` -> element [0][0] is 2, everything else 0, and regions
+    // without an in-bounds sample keep those values.
+    for (int k = 0; k < 8 * nsrc; ++k) ca[k] = 0.0f;
+    ca[0] = 2.0f;
+
+    const float depth_sigma = (F.depth_max - F.depth_min) / 64.0f;
+    const float two_ds2 = 2 * depth_sigma * depth_sigma;
+    const float angle_sigma = PM_PI_F * (5.0f / 180.0f);
+    const float two_as2 = 2 * angle_sigma * angle_sigma;
+
+    const pm_f4 cur = S.planes[idx];
+    PmWeights vw = {0ull, 0ull};
+    uint32_t sel = 0;
+    float wnorm = 0.f;
+    float fc[8];
+    int kmin = 0;
+    float cost_now = 0.f, g_now = 0.f, depth_now = 0.f, restricted_cost = 0.f;
+    pm_f4 plane_now = cur;
+    // refinement proposal ingredients (set at h == 9)
+    float depth_rand = 0.f, depth_pert = 0.f, depth_base = 0.f, depth_prior = 0.f;
+    pm_f4 rand_n = cur, pert_n = cur, base_n = cur, prior_pl = cur;
+    bool has_prior = false;
+
+#pragma unroll 1
+    for (int h = 0; h < 14; ++h) {
+        if (h == 8) {
+            // ---- view selection (cu:821-878)
+            uint32_t nb[4];  // neighbour masks: up / down / left / right, gated by the flags of regions 0..3 (cu:824-830)
+            nb[0] = (flags & 1u) ? S.views[idx - W] : 0u;
+            nb[1] = (flags & 2u) ? S.views[idx + W] : 0u;
+            nb[2] = (flags & 4u) ? S.views[idx - 1] : 0u;
+            nb[3] = (flags & 8u) ? S.views[idx + 1] : 0u;
+            const float thr = (float)(0.8 * (double)pm_exp((float)(iter * iter) / (-90.0f)));
+            const float fallback = pm_exp(thr * thr / (-0.32f));
+            float probs[PM_MAX_SRC];
+            float psum = 0.f;
+            for (int v = 0; v < nsrc; ++v) {
+                float prior = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if ((flags >> i) & 1u) prior += ((nb[i] >> v) & 1u) ? 0.9f : 0.1f;
+                float count = 0.f, tmpw = 0.f; int count_false = 0;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const float cc = ca[r * nsrc + v];
+                    if (cc < thr) { tmpw += pm_exp(cc * cc / (-0.18f)); count += 1.f; }
+                    if (cc > 1.2f) ++count_false;
+                }
+                float pr;
+                if (count > 2 && count_false < 3) pr = prior * tmpw / count;
+                else if (count_false < 3) pr = prior * fallback;
+                else pr = 0.f;
+                probs[v] = pr;
+                psum += pr;
+            }
+            // TransformPDFToCDF, cu:42-56 (0-sum -> NaNs, last bin forced to 1)
+            const float inv = 1.0f / psum;
+            float cum = 0.f;
+            for (int v = 0; v < nsrc; ++v) { cum += probs[v] * inv; probs[v] = cum; }
+            probs[nsrc - 1] = 1.f;
+            for (int s = 0; s < 15; ++s) {
+                const float u = pm_uniform(rs) - FLT_EPSILON;
+                for (int v = 0; v < nsrc; ++v)
+                    if (probs[v] > u) { vw.inc(v); break; }
+            }
+            for (int v = 0; v < nsrc; ++v) {
+                const int wv = vw.get(v);
+                if (wv > 0) { sel |= 1u << v; wnorm += (float)wv; }
+            }
+            // ---- candidate scores (cu:880-899)
+#pragma unroll 1
+            for (int r = 0; r < 8; ++r) {
+                float acc = 0.f;
+                const bool fl = (flags >> r) & 1u;
+                pm_f4 pl = cur;
+                if (F.geom && fl) pl = S.planes[pos[r]];
+                for (uint32_t m = sel; m; m &= m - 1) {
+                    const int v = pm_ffs(m) - 1;
+                    float term = ca[r * nsrc + v];
+                    if (F.geom) term += fl ? 0.2f * pm_geom_cost(c, F, v, pl, x, y) : 0.1f * 3.0f;
+                    acc += (float)vw.get(v) * term;
+                }
+                fc[r] = acc / wnorm;
+            }
+            float mn = fc[0];  // FindMinCostIndex, cu:58-69: last minimum wins
+#pragma unroll
+            for (int r = 1; r < 8; ++r) if (fc[r] <= mn) { mn = fc[r]; kmin = r; }
+        }
+        if (h == 9) {
+            // ---- planar-prior selection (cu:924-978)
+            if (F.planar && !F.geom) {
+                if (S.mask[idx] > 0) {
+                    const pm_f4 pp = S.prior[idx];
+                    const float dprior = pm_depth_from_plane(F, pp, x, y);
+                    float rbest = 0.f; int kmax = 0;   // FindMaxCostIndex (0 for unflagged), last max wins
+                    pm_f4 cand_best = cur;
+#pragma unroll 1
+                    for (int r = 0; r < 8; ++r) {
+                        float rf = 0.f;
+                        pm_f4 pl = cur;
+                        if ((flags >> r) & 1u) {
+                            pl = S.planes[pos[r]];
+                            const float dd = pm_depth_from_plane(F, pl, x, y) - dprior;
+                            const float ad = acosf(pm_dot3(pp, pl));
+                            const float prior = 0.5f + pm_exp(-dd * dd / two_ds2) * pm_exp(-ad * ad / two_as2);
+                            rf = pm_exp(-fc[r] * fc[r] / 0.18f) * prior;
+                        }
+                        if (r == 0 || rf >= rbest) { rbest = rf; kmax = r; cand_best = pl; }
+                    }
+                    const float dd = depth_now - dprior;
+                    const float ad = acosf(pm_dot3(pp, cur));
+                    const float prior = 0.5f + pm_exp(-dd * dd / two_ds2) * pm_exp(-ad * ad / two_as2);
+                    const float rc_now = pm_exp(-cost_now * cost_now / 0.18f) * prior;
+                    if ((flags >> kmax) & 1u) {
+                        const float db = pm_depth_from_plane(F, cand_best, x, y);
+                        if (db >= F.depth_min && db <= F.depth_max && rbest > rc_now) {
+                            // QUIRK cu:950-966: the adopted depth goes to a shadowed local and cost_now is not
+                            // updated: refinement continues with the OLD depth and OLD cost but the NEW plane.
+                            plane_now = cand_best;
+                            restricted_cost = rbest;
+                            S.views[idx] = sel;
+                        }
+                    }
+                } else if ((flags >> kmin) & 1u) {
+                    const pm_f4 pl = S.planes[pos[kmin]];
+                    const float db = pm_depth_from_plane(F, pl, x, y);
+                    if (db >= F.depth_min && db <= F.depth_max && fc[kmin] < cost_now) {
+                        // QUIRK cu:969-977: plane and depth adopted, cost_now and the view mask are not
+                        depth_now = db;
+                        plane_now = pl;
+                    }
+                }
+            }
+            // ---- plain selection (cu:981-991)
+            if (!F.planar && ((flags >> kmin) & 1u)) {
+                const pm_f4 pl = S.planes[pos[kmin]];
+                const float db = pm_depth_from_plane(F, pl, x, y);
+                if (db >= F.depth_min && db <= F.depth_max && fc[kmin] < cost_now) {
+                    depth_now = db; plane_now = pl; cost_now = fc[kmin];
+                    S.views[idx] = sel;
+                }
+            }
+            // ---- refinement proposals (cu:644-675)
+            const float perturbation = 0.02f;
+            has_prior = F.planar && S.mask[idx] > 0;
+            if (has_prior) {
+                // QUIRK cu:656-663: the prior-guided proposal is drawn (4 uniforms) and then overwritten, because
+                // the block that follows has no `else`. Only the RNG stream advances.
+                prior_pl = S.prior[idx];
+                depth_prior = pm_depth_from_plane(F, prior_pl, x, y);
+                (void)pm_uniform(rs);
+                (void)pm_perturbed_normal(F, x, y, prior_pl, rs, angle_sigma);
+            }
+            depth_rand = pm_uniform(rs) * (F.depth_max - F.depth_min) + F.depth_min;
+            rand_n = pm_random_normal(F, x, y, rs);
+            // QUIRK cu:668-670: `while (d < min && d > max)` can never hold, so exactly one draw
+            const float dlo = (1 - perturbation) * depth_now, dhi = (1 + perturbation) * depth_now;
+            depth_pert = pm_uniform(rs) * (dhi - dlo) + dlo;
+            pert_n = pm_perturbed_normal(F, x, y, plane_now, rs, perturbation * PM_PI_F);
+            base_n = plane_now;
+            depth_base = depth_now;
+        }
+
+        // ---- the hypothesis of this iteration and the views it is scored on
+        pm_f4 tp;
+        uint32_t mask;
+        float hd = 0.f;
+        if (h < 8) {
+            if (!((flags >> h) & 1u)) continue;
+            tp = S.planes[pos[h]];
+            mask = all_views;                       // cu:817: every source view
+        } else if (h == 8) {
+            tp = cur;
+            mask = sel;                             // cu:903-913; zero-weight views contribute exactly 0
+        } else {
+            // (d_rand, n) (d, n_rand) (d_rand, n_rand) (d, n_pert) (d_pert, n)   cu:674-675
+            const int i = h - 9;
+            hd = (i == 0 || i == 2) ? depth_rand : (i == 4 ? depth_pert : depth_base);
+            tp = (i == 1 || i == 2) ? rand_n : (i == 3 ? pert_n : base_n);
+            tp.w = pm_plane_distance(F, x, y, hd, tp);
+            mask = sel;                             // cu:684-694
+        }
+        const PmHyp hyp = pm_hyp(F, tp, x, y);
+        float tc = 0.f, tg = 0.f;
+#pragma unroll 1
+        for (uint32_t m = mask; m; m &= m - 1) {
+            const int v = pm_ffs(m) - 1;
+            const float cst = pm_ncc<SCALE>(c, F, st, v, hyp, x, y, nexec);
+            if (h < 8) {
+                ca[h * nsrc + v] = cst;
+            } else {
+                const float wv = (float)vw.get(v);
+                if (F.geom) {
+                    const float g = 0.2f * pm_geom_cost(c, F, v, tp, x, y);
+                    tc += wv * (cst + g);
+                    // QUIRK cu:689: in refinement the geometric part is weighted by view_weights[hypothesis index]
+                    tg += (h == 8 ? wv : (float)vw.get(h - 9)) * g;
+                } else {
+                    tc += wv * cst;
+                }
+            }
+        }
+        if (h == 8) {
+            cost_now = tc / wnorm;
+            if (F.geom) g_now = tg / wnorm;
+            depth_now = pm_depth_from_plane(F, cur, x, y);
+        } else if (h > 8) {
+            tc /= wnorm;
+            if (F.geom) tg /= wnorm;
+            const float dbefore = pm_depth_from_plane(F, tp, x, y);
+            const bool in_range = dbefore >= F.depth_min && dbefore <= F.depth_max;
+            if (has_prior) {
+                const float dd = hd - depth_prior;
+                const float ad = acosf(pm_dot3(prior_pl, tp));
+                const float prior = 0.5f + pm_exp(-dd * dd / two_ds2) * pm_exp(-ad * ad / two_as2);
+                const float rtc = pm_exp(-tc * tc / 0.18f) * prior;
+                // QUIRK cu:707-710: restricted_cost is never refreshed after an accept
+                if (in_range && rtc > restricted_cost) { plane_now = tp; cost_now = tc; }
+            } else if (in_range && tc < cost_now) {
+                plane_now = tp; cost_now = tc; g_now = tg;
+            }
+        }
+    }
+    // ---- write-back (cu:993-997)
+    S.costs[idx] = cost_now;
+    S.planes[idx] = plane_now;
+    if (F.geom) S.geom[idx] = g_now;
+    pm_rng_store(S.rng, idx, rs);
+    if (S.counters) pm_count(S.counters, nexec);
+}
+
+// ------------------------------------------------------------------------------------------------ init / finalize
+// InitializeScore, cu:536-573 (always evaluated at the widest window, SCALE = max_scale = 2).
+template <int SCALE, class Ctx>
+PM_HD void pm_init_pixel(const Ctx& c, const PmFrame& F, const PmState& S, int x, int y, uint64_t seed) {
+    const int idx = y * F.W + x;
+    PmRng rs;
+    pm_rng_init(rs, pm_mix_seed(seed, (uint32_t)x, (uint32_t)y));
+    pm_f4 pl;
+    if (!F.geom && !F.planar) {
+        pl = pm_random_plane(F, x, y, rs);
+    } else if (F.planar && S.mask[idx] > 0 && S.costs[idx] >= 0.1f) {
+        // prior-guided re-initialisation: plane distance uniform in [0.94, 1.06] * w_prior, normal perturbed by 0.06 pi
+        const float perturbation = 0.02f;
+        const pm_f4 pp = S.prior[idx];
+        const float lo = (1 - 3 * perturbation) * pp.w, hi = (1 + 3 * perturbation) * pp.w;
+        const float dp = pm_uniform(rs) * (hi - lo) + lo;
+        pl = pm_perturbed_normal(F, x, y, pp, rs, 3 * perturbation * PM_PI_F);
+        pl.w = dp;
+    } else {
+        // stored (world normal, depth) -> (camera normal, plane distance)
+        const pm_f4 q = S.planes[idx];
+        pl.x = F.R[0] * q.x + F.R[1] * q.y + F.R[2] * q.z;
+        pl.y = F.R[3] * q.x + F.R[4] * q.y + F.R[5] * q.z;
+        pl.z = F.R[6] * q.x + F.R[7] * q.y + F.R[8] * q.z;
+        pl.w = pm_plane_distance(F, x, y, q.w, pl);
+    }
+    const PmRefStats st = pm_ref_stats<SCALE>(c, F);
+    uint32_t sel, nexec = 0;
+    const float cost = pm_initial_cost<SCALE>(c, F, st, pl, x, y, sel, nexec);
+    S.planes[idx] = pl;
+    S.costs[idx] = cost;
+    S.views[idx] = sel;
+    pm_rng_store(S.rng, idx, rs);
+    if (S.counters) pm_count(S.counters, nexec);
+}
+
+// GetDepthandNormal, cu:1021-1034
+PM_HD pm_f4 pm_depth_normal(const PmFrame& F, const pm_f4& pl, int x, int y) {
+    pm_f4 o;
+    o.w = pm_depth_from_plane(F, pl, x, y);
+    o.x = F.R[0] * pl.x + F.R[3] * pl.y + F.R[6] * pl.z;
+    o.y = F.R[1] * pl.x + F.R[4] * pl.y + F.R[7] * pl.z;
+    o.z = F.R[2] * pl.x + F.R[5] * pl.y + F.R[8] * pl.z;
+    return o;
+}
+
+// CheckerboardFilter, cu:1036-1150: median of the depth over the pixel and up to 20 opposite-colour neighbours.
+// Returns the filtered depth (or the unchanged one when cost < 0.001).
+PM_HD float pm_median_depth(const pm_f4* planes, const float* costs, int W, int H, int x, int y) {
+    const int ctr = y * W + x;
+    const float self = planes[ctr].w;
+    if (costs[ctr] < 0.001f) return self;
+    float f[21];
+    int n = 0;
+    f[n++] = self;
+#define PM_TAP(cond, off) if (cond) f[n++] = planes[ctr + (off)].w;
+    PM_TAP(y > 0, -W) PM_TAP(y > 2, -3 * W) PM_TAP(y > 4, -5 * W)
+    PM_TAP(y < H - 1, W) PM_TAP(y < H - 3, 3 * W) PM_TAP(y < H - 5, 5 * W)
+    PM_TAP(x > 0, -1) PM_TAP(x > 2, -3) PM_TAP(x > 4, -5)
+    PM_TAP(x < W - 1, 1) PM_TAP(x < W - 3, 3) PM_TAP(x < W - 5, 5)
+    // knight-like taps; bounds tests are the reference's, asymmetries included (cu:1107-1141)
+    PM_TAP(y > 0 && x < W - 2, -W + 2) PM_TAP(y < H - 1 && x < W - 2, W + 2)
+    PM_TAP(y > 0 && x > 1, -W - 2) PM_TAP(y < H - 1 && x > 1, W - 2)
+    PM_TAP(x > 0 && y > 2, -1 - 2 * W) PM_TAP(x < W - 1 && y > 2, 1 - 2 * W)
+    PM_TAP(x > 0 && y < H - 2, -1 + 2 * W) PM_TAP(x < W - 1 && y < H - 2, 1 + 2 * W)
+#undef PM_TAP
+    for (int i = 1; i < n; ++i) {  // insertion sort, cu:14-23
+        const float t = f[i];
+        int j = i;
+        for (; j >= 1 && t < f[j - 1]; --j) f[j] = f[j - 1];
+        f[j] = t;
+    }
+    const int m = n / 2;
+    return (n % 2 == 0) ? (f[m - 1] + f[m]) / 2 : f[m];
+}
+
+#endif  // MPMVS_PM_CORE_CUH

@@ -1,0 +1,268 @@
+// pm_kernels.cu -- sm_100a kernels of the PatchMatch path and their launchers.
+//
+// Kernels (reference counterparts in /root/reference/src/PatchMatch.cu):
+//   pm_init_kernel<2>        InitializeScore                 cu:536-573
+//   pm_sweep_kernel<S>       BlackPixelUpdate/RedPixelUpdate cu:724-1019   (S = window scale 0/1/2)
+//   pm_depth_normal_kernel   GetDepthandNormal               cu:1021-1034
+//   pm_filter_kernel         Black/RedPixelFilter            cu:1036-1174
+//   pm_ncc_map_kernel<S>, pm_geom_map_kernel                 test hooks over pm_ncc / pm_geom_cost
+//   pm_export_depth_kernel   depth channel -> dense map (feeds the inter-GPU depth all-gather)
+//
+// Block = 32 x 8 threads, one thread per pixel. A sweep block owns a 32 x 16 pixel tile of one
+// checkerboard colour; the reference-image window of the tile (tile + 5*2^S halo) is staged once in
+// shared memory through the texture unit (exact texel fetch, hardware clamp-to-edge at the borders),
+// the per-view constants sit next to it. Source samples go through the texture unit: they are
+// homography-warped scattered bilinear reads, which is what the unit is built for, and it keeps the
+// reference's 9-bit-weight filtering bit-for-bit.
+#include <cuda_runtime.h>
+
+#include "pm_core.cuh"
+#include "pm_kernels.h"
+
+namespace {
+
+constexpr int BW = 32, BH = 8;
+constexpr int MIN_BLOCKS = 3;  // 3 x 256 threads per SM -> at most 85 registers per thread
+
+template <int SCALE, int ROWS>
+struct Tile {
+    static constexpr int R = 5 << SCALE;      // halo = largest tap offset
+    static constexpr int TW = BW + 2 * R;     // 42 / 52 / 72
+    static constexpr int TH = ROWS + 2 * R;
+    static constexpr int PITCH = TW;          // even pitch: a checkerboard warp alternates rows r, r+1 with x -> even lanes hit
+                                              // even banks, odd lanes odd banks (conflict-free); an odd pitch would 2-way conflict
+    static constexpr int FLOATS = PITCH * TH;
+};
+
+template <int PITCH, bool SOFT_CLAMP>
+struct DevCtx {
+    const float* centre;   // shared-memory address of this thread's pixel inside the tile
+    const PmView* views;   // shared memory
+    cudaTextureObject_t tex;
+    __device__ __forceinline__ float ref(int dx, int dy) const { return centre[dy * PITCH + dx]; }
+    __device__ __forceinline__ float src(int v, float xs, float ys) const {
+        const PmView& V = views[v];
+        if (SOFT_CLAMP) {  // views smaller than the layered array: hardware clamp would hit the padding
+            xs = fminf(fmaxf(xs, 0.5f), V.w - 0.5f);
+            ys = fminf(fmaxf(ys, 0.5f), V.h - 0.5f);
+        }
+        return tex2DLayered<float>(tex, xs, ys, V.layer);
+    }
+    __device__ __forceinline__ float src_depth(int v, int xi, int yi) const {
+        const PmView& V = views[v];
+        xi = min(max(xi, 0), V.dw - 1);
+        yi = min(max(yi, 0), V.dh - 1);
+        return __ldg(V.depth + (size_t)yi * V.dpitch + xi);
+    }
+    __device__ __forceinline__ const PmView& view(int v) const { return views[v]; }
+};
+
+// cooperative staging: per-view constants, then the reference window of the tile whose top-left pixel is (x0, y0)
+template <int SCALE, int ROWS>
+__device__ __forceinline__ void stage_tile(float* tile, PmView* sviews, const PmView* gviews, const PmFrame& F,
+                                           int x0, int y0) {
+    using T = Tile<SCALE, ROWS>;
+    const int tid = threadIdx.y * BW + threadIdx.x;
+    {
+        const uint32_t* g = reinterpret_cast<const uint32_t*>(gviews);
+        uint32_t* s = reinterpret_cast<uint32_t*>(sviews);
+        const int words = F.nsrc * (int)(sizeof(PmView) / 4);
+        for (int i = tid; i < words; i += BW * BH) s[i] = __ldg(g + i);
+    }
+    for (int i = tid; i < T::TW * T::TH; i += BW * BH) {
+        const int ty = i / T::TW, tx = i - ty * T::TW;
+        // exact texel fetch (weights 1/0 at texel centres); clamp-to-edge like the reference's texture (PatchMatch.cpp:1012-1018)
+        const int gx = min(max(x0 - T::R + tx, 0), F.W - 1), gy = min(max(y0 - T::R + ty, 0), F.H - 1);
+        tile[ty * T::PITCH + tx] = tex2DLayered<float>((cudaTextureObject_t)F.tex, (float)gx + 0.5f, (float)gy + 0.5f, F.ref_layer);
+    }
+    __syncthreads();
+}
+
+template <int SCALE, bool CL>
+__global__ void __launch_bounds__(BW* BH, MIN_BLOCKS) pm_sweep_kernel(const PmFrame F, const PmState S, const PmView* gviews,
+                                                           int red, int iter) {
+    using T = Tile<SCALE, 2 * BH>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PmView* sviews = reinterpret_cast<PmView*>(smem_raw);
+    float* tile = reinterpret_cast<float*>(smem_raw + PM_MAX_SRC * sizeof(PmView));
+    const int x0 = blockIdx.x * BW, y0 = blockIdx.y * 2 * BH;
+    stage_tile<SCALE, 2 * BH>(tile, sviews, gviews, F, x0, y0);
+    const int tx = threadIdx.x, ly = 2 * threadIdx.y + ((tx & 1) ^ red);
+    const int x = x0 + tx, y = y0 + ly;
+    if (x >= F.W || y >= F.H) return;
+    DevCtx<T::PITCH, CL> c;
+    c.centre = tile + (ly + T::R) * T::PITCH + (tx + T::R);
+    c.views = sviews;
+    c.tex = (cudaTextureObject_t)F.tex;
+    float ca[8 * PM_MAX_SRC];
+    pm_sweep_pixel<SCALE>(c, F, S, x, y, iter, ca);
+}
+
+template <int SCALE, bool CL>
+__global__ void __launch_bounds__(BW* BH, MIN_BLOCKS) pm_init_kernel(const PmFrame F, const PmState S, const PmView* gviews,
+                                                          unsigned long long seed) {
+    using T = Tile<SCALE, BH>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PmView* sviews = reinterpret_cast<PmView*>(smem_raw);
+    float* tile = reinterpret_cast<float*>(smem_raw + PM_MAX_SRC * sizeof(PmView));
+    const int x0 = blockIdx.x * BW, y0 = blockIdx.y * BH;
+    stage_tile<SCALE, BH>(tile, sviews, gviews, F, x0, y0);
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= F.W || y >= F.H) return;
+    DevCtx<T::PITCH, CL> c;
+    c.centre = tile + (threadIdx.y + T::R) * T::PITCH + (threadIdx.x + T::R);
+    c.views = sviews;
+    c.tex = (cudaTextureObject_t)F.tex;
+    pm_init_pixel<SCALE>(c, F, S, x, y, seed);
+}
+
+template <int SCALE, bool CL>
+__global__ void __launch_bounds__(BW* BH, MIN_BLOCKS) pm_ncc_map_kernel(const PmFrame F, const PmView* gviews,
+                                                             const pm_f4* planes, float* out) {
+    using T = Tile<SCALE, BH>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PmView* sviews = reinterpret_cast<PmView*>(smem_raw);
+    float* tile = reinterpret_cast<float*>(smem_raw + PM_MAX_SRC * sizeof(PmView));
+    const int x0 = blockIdx.x * BW, y0 = blockIdx.y * BH;
+    stage_tile<SCALE, BH>(tile, sviews, gviews, F, x0, y0);
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= F.W || y >= F.H) return;
+    DevCtx<T::PITCH, CL> c;
+    c.centre = tile + (threadIdx.y + T::R) * T::PITCH + (threadIdx.x + T::R);
+    c.views = sviews;
+    c.tex = (cudaTextureObject_t)F.tex;
+    const int idx = y * F.W + x;
+    const PmRefStats st = pm_ref_stats<SCALE>(c, F);
+    const PmHyp hyp = pm_hyp(F, planes[idx], x, y);
+    uint32_t nexec = 0;
+    for (int v = 0; v < F.nsrc; ++v) out[(size_t)v * F.W * F.H + idx] = pm_ncc<SCALE>(c, F, st, v, hyp, x, y, nexec);
+}
+
+__global__ void __launch_bounds__(BW* BH) pm_geom_map_kernel(const PmFrame F, const PmView* gviews, const pm_f4* planes,
+                                                              float* out) {
+    __shared__ PmView sviews[PM_MAX_SRC];
+    {
+        const int tid = threadIdx.y * BW + threadIdx.x;
+        const uint32_t* g = reinterpret_cast<const uint32_t*>(gviews);
+        uint32_t* s = reinterpret_cast<uint32_t*>(sviews);
+        for (int i = tid; i < F.nsrc * (int)(sizeof(PmView) / 4); i += BW * BH) s[i] = g[i];
+        __syncthreads();
+    }
+    const int x = blockIdx.x * BW + threadIdx.x, y = blockIdx.y * BH + threadIdx.y;
+    if (x >= F.W || y >= F.H) return;
+    DevCtx<1, false> c;
+    c.centre = nullptr;
+    c.views = sviews;
+    c.tex = (cudaTextureObject_t)F.tex;
+    const int idx = y * F.W + x;
+    for (int v = 0; v < F.nsrc; ++v) out[(size_t)v * F.W * F.H + idx] = pm_geom_cost(c, F, v, planes[idx], x, y);
+}
+
+__global__ void __launch_bounds__(256) pm_depth_normal_kernel(const PmFrame F, pm_f4* planes) {
+    const int x = blockIdx.x * BW + threadIdx.x, y = blockIdx.y * BH + threadIdx.y;
+    if (x >= F.W || y >= F.H) return;
+    const int idx = y * F.W + x;
+    planes[idx] = pm_depth_normal(F, planes[idx], x, y);
+}
+
+__global__ void __launch_bounds__(256) pm_filter_kernel(const PmFrame F, pm_f4* planes, const float* costs, int red) {
+    const int tx = threadIdx.x;
+    const int x = blockIdx.x * BW + tx;
+    const int y = 2 * (blockIdx.y * BH + threadIdx.y) + ((tx & 1) ^ red);
+    if (x >= F.W || y >= F.H) return;
+    planes[y * F.W + x].w = pm_median_depth(planes, costs, F.W, F.H, x, y);
+}
+
+__global__ void __launch_bounds__(256) pm_export_depth_kernel(const pm_f4* planes, float* out, int W, int H, int pitch_f) {
+    const int x = blockIdx.x * BW + threadIdx.x, y = blockIdx.y * BH + threadIdx.y;
+    if (x >= W || y >= H) return;
+    out[(size_t)y * pitch_f + x] = planes[y * W + x].w;
+}
+
+__global__ void pm_uniform_stream_kernel(unsigned long long seed, int x, int y, int n, float* out) {
+    PmRng rs;
+    pm_rng_init(rs, pm_mix_seed(seed, (uint32_t)x, (uint32_t)y));
+    for (int i = 0; i < n; ++i) out[i] = pm_uniform(rs);
+}
+
+template <int SCALE, int ROWS>
+constexpr size_t smem_bytes() {
+    return PM_MAX_SRC * sizeof(PmView) + Tile<SCALE, ROWS>::FLOATS * sizeof(float);
+}
+
+inline dim3 grid_full(int W, int H) { return dim3((W + BW - 1) / BW, (H + BH - 1) / BH, 1); }
+// Same row coverage as the reference's 32x16 blocks over H/2 rows (cu:1196): 16*ceil((H/2)/16) thread rows.
+inline dim3 grid_checker(int W, int H) { return dim3((W + BW - 1) / BW, 2 * (((H / 2) + 15) / 16), 1); }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------- launchers
+cudaError_t pm_launch_init(const PmFrame& F, const PmState& S, const PmView* gviews, unsigned long long seed, cudaStream_t st) {
+    if (F.soft_clamp) pm_init_kernel<2, true><<<grid_full(F.W, F.H), dim3(BW, BH), smem_bytes<2, BH>(), st>>>(F, S, gviews, seed);
+    else pm_init_kernel<2, false><<<grid_full(F.W, F.H), dim3(BW, BH), smem_bytes<2, BH>(), st>>>(F, S, gviews, seed);
+    return cudaGetLastError();
+}
+
+cudaError_t pm_launch_sweep(const PmFrame& F, const PmState& S, const PmView* gviews, int red, int iter, int scale,
+                            cudaStream_t st) {
+    const dim3 g = grid_checker(F.W, F.H), b(BW, BH);
+    switch (scale) {
+        case 0:
+            if (F.soft_clamp) pm_sweep_kernel<0, true><<<g, b, smem_bytes<0, 2 * BH>(), st>>>(F, S, gviews, red, iter);
+            else pm_sweep_kernel<0, false><<<g, b, smem_bytes<0, 2 * BH>(), st>>>(F, S, gviews, red, iter);
+            break;
+        case 1:
+            if (F.soft_clamp) pm_sweep_kernel<1, true><<<g, b, smem_bytes<1, 2 * BH>(), st>>>(F, S, gviews, red, iter);
+            else pm_sweep_kernel<1, false><<<g, b, smem_bytes<1, 2 * BH>(), st>>>(F, S, gviews, red, iter);
+            break;
+        case 2:
+            if (F.soft_clamp) pm_sweep_kernel<2, true><<<g, b, smem_bytes<2, 2 * BH>(), st>>>(F, S, gviews, red, iter);
+            else pm_sweep_kernel<2, false><<<g, b, smem_bytes<2, 2 * BH>(), st>>>(F, S, gviews, red, iter);
+            break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t pm_launch_finalize(const PmFrame& F, const PmState& S, cudaStream_t st) {
+    pm_depth_normal_kernel<<<grid_full(F.W, F.H), dim3(BW, BH), 0, st>>>(F, S.planes);
+    pm_filter_kernel<<<grid_checker(F.W, F.H), dim3(BW, BH), 0, st>>>(F, S.planes, S.costs, 0);
+    pm_filter_kernel<<<grid_checker(F.W, F.H), dim3(BW, BH), 0, st>>>(F, S.planes, S.costs, 1);
+    return cudaGetLastError();
+}
+
+cudaError_t pm_launch_ncc_map(const PmFrame& F, const PmView* gviews, const pm_f4* planes, int scale, float* out,
+                              cudaStream_t st) {
+    const dim3 g = grid_full(F.W, F.H), b(BW, BH);
+    switch (scale) {
+        case 0:
+            if (F.soft_clamp) pm_ncc_map_kernel<0, true><<<g, b, smem_bytes<0, BH>(), st>>>(F, gviews, planes, out);
+            else pm_ncc_map_kernel<0, false><<<g, b, smem_bytes<0, BH>(), st>>>(F, gviews, planes, out);
+            break;
+        case 1:
+            if (F.soft_clamp) pm_ncc_map_kernel<1, true><<<g, b, smem_bytes<1, BH>(), st>>>(F, gviews, planes, out);
+            else pm_ncc_map_kernel<1, false><<<g, b, smem_bytes<1, BH>(), st>>>(F, gviews, planes, out);
+            break;
+        case 2:
+            if (F.soft_clamp) pm_ncc_map_kernel<2, true><<<g, b, smem_bytes<2, BH>(), st>>>(F, gviews, planes, out);
+            else pm_ncc_map_kernel<2, false><<<g, b, smem_bytes<2, BH>(), st>>>(F, gviews, planes, out);
+            break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t pm_launch_geom_map(const PmFrame& F, const PmView* gviews, const pm_f4* planes, float* out, cudaStream_t st) {
+    pm_geom_map_kernel<<<grid_full(F.W, F.H), dim3(BW, BH), 0, st>>>(F, gviews, planes, out);
+    return cudaGetLastError();
+}
+
+cudaError_t pm_launch_export_depth(const pm_f4* planes, float* out, int W, int H, int pitch_floats, cudaStream_t st) {
+    pm_export_depth_kernel<<<grid_full(W, H), dim3(BW, BH), 0, st>>>(planes, out, W, H, pitch_floats);
+    return cudaGetLastError();
+}
+
+cudaError_t pm_launch_uniform_stream(unsigned long long seed, int x, int y, int n, float* out, cudaStream_t st) {
+    pm_uniform_stream_kernel<<<1, 1, 0, st>>>(seed, x, y, n, out);
+    return cudaGetLastError();
+}

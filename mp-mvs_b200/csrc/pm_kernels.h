@@ -1,0 +1,17 @@
+// pm_kernels.h -- launchers of the sm_100a kernels (pm_kernels.cu), used by the C-ABI layer (pm_capi.cu).
+#ifndef MPMVS_PM_KERNELS_H
+#define MPMVS_PM_KERNELS_H
+#include <cuda_runtime.h>
+
+#include "pm_core.cuh"
+
+cudaError_t pm_launch_init(const PmFrame& F, const PmState& S, const PmView* gviews, unsigned long long seed, cudaStream_t st);
+cudaError_t pm_launch_sweep(const PmFrame& F, const PmState& S, const PmView* gviews, int red, int iter, int scale,
+                            cudaStream_t st);
+cudaError_t pm_launch_finalize(const PmFrame& F, const PmState& S, cudaStream_t st);
+cudaError_t pm_launch_ncc_map(const PmFrame& F, const PmView* gviews, const pm_f4* planes, int scale, float* out,
+                              cudaStream_t st);
+cudaError_t pm_launch_geom_map(const PmFrame& F, const PmView* gviews, const pm_f4* planes, float* out, cudaStream_t st);
+cudaError_t pm_launch_export_depth(const pm_f4* planes, float* out, int W, int H, int pitch_floats, cudaStream_t st);
+cudaError_t pm_launch_uniform_stream(unsigned long long seed, int x, int y, int n, float* out, cudaStream_t st);
+#endif

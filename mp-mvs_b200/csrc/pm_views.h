@@ -1,0 +1,95 @@
+// pm_views.h -- host-side preparation of the per-view constants (PmView) and the frame constants (PmFrame).
+// Plain C++ (no CUDA), double precision; used by pm_capi.cu and by the test-only host emulation.
+#ifndef MPMVS_PM_VIEWS_H
+#define MPMVS_PM_VIEWS_H
+#include "../../include/mpmvs_b200.h"
+#include "pm_core.cuh"
+
+namespace pmv {
+// ---- small double-precision 3x3 helpers for the per-view constants
+struct M3 { double m[9]; };
+inline M3 mul(const M3& a, const M3& b) {
+    M3 r;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) r.m[3 * i + j] = a.m[3 * i] * b.m[j] + a.m[3 * i + 1] * b.m[3 + j] + a.m[3 * i + 2] * b.m[6 + j];
+    return r;
+}
+inline M3 transpose(const M3& a) {
+    M3 r;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) r.m[3 * i + j] = a.m[3 * j + i];
+    return r;
+}
+inline void mulv(const M3& a, const double* v, double* o) {
+    for (int i = 0; i < 3; ++i) o[i] = a.m[3 * i] * v[0] + a.m[3 * i + 1] * v[1] + a.m[3 * i + 2] * v[2];
+}
+inline M3 from(const float* f) {
+    M3 r;
+    for (int i = 0; i < 9; ++i) r.m[i] = f[i];
+    return r;
+}
+// the zero-skew inverse intrinsics the reference uses when it back-projects (cu:163-168, 260-268, 587-588)
+inline M3 kinv_zero_skew(const float* K) {
+    M3 r = {{1.0 / K[0], 0, -(double)K[2] / K[0], 0, 1.0 / K[4], -(double)K[5] / K[4], 0, 0, 1}};
+    return r;
+}
+// the part of K_s the homography uses (cu:270-278): fx, cx, fy, cy and K[8]
+inline M3 k_homography(const float* K) {
+    M3 r = {{K[0], 0, K[2], 0, K[4], K[5], 0, 0, K[8]}};
+    return r;
+}
+
+}  // namespace pmv
+
+inline void pm_build_view_consts(const mpmvs_camera& rc, const mpmvs_camera& sc, PmView& V) {
+    using namespace pmv;
+    const M3 Rr = from(rc.R), Rs = from(sc.R);
+    const M3 Rrel = mul(Rs, transpose(Rr));                  // R_s R_r^T          (cu:233-241)
+    const double Crel[3] = {(double)rc.C[0] - sc.C[0], (double)rc.C[1] - sc.C[1], (double)rc.C[2] - sc.C[2]};
+    double trel[3];
+    mulv(Rs, Crel, trel);                                    // R_s (C_r - C_s)    (cu:242-247)
+    const M3 Kri = kinv_zero_skew(rc.K), Ksh = k_homography(sc.K);
+    const M3 A = mul(Ksh, mul(Rrel, Kri));
+    double b[3];
+    mulv(Ksh, trel, b);
+    for (int i = 0; i < 9; ++i) V.A[i] = (float)A.m[i];
+    for (int i = 0; i < 3; ++i) V.b[i] = (float)(-b[i]);
+    V.w = (float)sc.width;
+    V.h = (float)sc.height;
+    // geometric consistency: forward  x_s ~ K_s (R_s (R_r^T (z K_r^-1 p) + C_r) + t_s)   (cu:582-615, full K in ProjectPoint)
+    const M3 Ksf = from(sc.K), Krf = from(rc.K);
+    const M3 Mf = mul(Ksf, mul(Rrel, Kri));
+    double tmp[3], Cr[3] = {rc.C[0], rc.C[1], rc.C[2]}, Cs[3] = {sc.C[0], sc.C[1], sc.C[2]}, vf[3], vb[3];
+    mulv(Rs, Cr, tmp);
+    for (int i = 0; i < 3; ++i) tmp[i] += sc.t[i];
+    mulv(Ksf, tmp, vf);
+    // backward  x_r ~ K_r (R_r (R_s^T (z_s K_s^-1 q) + C_s) + t_r)
+    const M3 Mb = mul(Krf, mul(transpose(Rrel), kinv_zero_skew(sc.K)));
+    mulv(Rr, Cs, tmp);
+    for (int i = 0; i < 3; ++i) tmp[i] += rc.t[i];
+    mulv(Krf, tmp, vb);
+    for (int i = 0; i < 9; ++i) { V.Mf[i] = (float)Mf.m[i]; V.Mb[i] = (float)Mb.m[i]; }
+    for (int i = 0; i < 3; ++i) { V.vf[i] = (float)vf[i]; V.vb[i] = (float)vb[i]; }
+    V.dw = sc.width;
+    V.dh = sc.height;
+    V.dpitch = sc.width;
+    V.depth = nullptr;
+}
+
+
+inline PmFrame pm_make_frame(const mpmvs_camera& c, int n, float depth_min, float depth_max, float sigma_spatial,
+                             float sigma_color, int top_k, bool geom, bool planar) {
+    PmFrame F{};
+    F.fx = c.K[0]; F.fy = c.K[4]; F.cx = c.K[2]; F.cy = c.K[5];
+    F.ifx = 1.0f / c.K[0]; F.ify = 1.0f / c.K[4];
+    F.fx_over_fy = c.K[0] / c.K[4];
+    for (int i = 0; i < 9; ++i) F.R[i] = c.R[i];
+    F.depth_min = depth_min; F.depth_max = depth_max;
+    const double log2e = 1.4426950408889634;
+    F.spat_k = (float)(-log2e / (2.0 * sigma_spatial * sigma_spatial));
+    F.col_k = (float)(log2e / (2.0 * sigma_color * sigma_color));
+    F.W = c.width; F.H = c.height; F.nsrc = n - 1; F.top_k = top_k;
+    F.geom = geom ? 1 : 0; F.planar = planar ? 1 : 0;
+    return F;
+}
+#endif

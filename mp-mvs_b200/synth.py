@@ -219,14 +219,31 @@ def _jpeg_roundtrip(gray: np.ndarray, quality: int = 97) -> Tuple[np.ndarray, by
     return dec, buf.tobytes()
 
 
-def _finish(name, width, height, faces, Ks, poses, pairs, jpeg=True, views: Optional[Sequence[int]] = None) -> SyntheticScene:
-    """Render the requested views (all by default); unrendered views keep empty placeholders."""
+def _render_one(args):
+    faces, K, R, t, width, height, jpeg = args
+    gray, depth, nrm = render_view(faces, K, R, t, width, height)
+    img = _jpeg_roundtrip(gray)[0] if jpeg else np.clip(np.rint(gray), 0, 255).astype(np.uint8)
+    return img, depth, nrm
+
+
+def _finish(name, width, height, faces, Ks, poses, pairs, jpeg=True, views: Optional[Sequence[int]] = None,
+            workers: int = 0) -> SyntheticScene:
+    """Render the requested views (all by default); unrendered views keep empty placeholders.
+
+    workers > 1 renders views in a fork()ed process pool (full-size scenes take ~15 s per view on one core)."""
     cams, images, gtd, gtn = [], [], [], []
-    want = set(range(len(poses))) if views is None else set(views)
+    want = sorted(set(range(len(poses))) if views is None else set(views))
+    jobs = [(list(faces), Ks[i], poses[i][0], poses[i][1], width, height, jpeg) for i in want]
+    if workers > 1 and len(jobs) > 1:
+        import multiprocessing as mp
+
+        with mp.get_context("fork").Pool(min(workers, len(jobs))) as pool:
+            rendered = dict(zip(want, pool.map(_render_one, jobs)))
+    else:
+        rendered = {i: _render_one(j) for i, j in zip(want, jobs)}
     for i, (K, (R, t)) in enumerate(zip(Ks, poses)):
-        if i in want:
-            gray, depth, nrm = render_view(faces, K, R, t, width, height)
-            img = _jpeg_roundtrip(gray)[0] if jpeg else np.clip(np.rint(gray), 0, 255).astype(np.uint8)
+        if i in rendered:
+            img, depth, nrm = rendered[i]
             valid = depth > 0
             dmin = float(depth[valid].min()) if valid.any() else 1.0
             dmax = float(depth[valid].max()) if valid.any() else 2.0
@@ -275,7 +292,7 @@ def _table_scene_faces(seed: int) -> List[Face]:
     return faces
 
 
-def make_dtu_scene(width=1600, height=1200, grid=7, n_src=10, seed=2, jpeg=True, views=None) -> SyntheticScene:
+def make_dtu_scene(width=1600, height=1200, grid=7, n_src=10, seed=2, jpeg=True, views=None, workers=0) -> SyntheticScene:
     """Config 2: DTU-shaped, grid x grid views on a spherical cap over boxes on a table."""
     f = 2890.0 * width / 1600.0
     K = _intrinsics(f, width, height)
@@ -290,10 +307,10 @@ def make_dtu_scene(width=1600, height=1200, grid=7, n_src=10, seed=2, jpeg=True,
     eyes = np.array(eyes)
     poses = [look_at(e, target) for e in eyes]
     pairs = _nearest_pairs(eyes, target, n_src)
-    return _finish("dtu", width, height, faces, [K] * len(eyes), poses, pairs, jpeg, views)
+    return _finish("dtu", width, height, faces, [K] * len(eyes), poses, pairs, jpeg, views, workers)
 
 
-def make_eth3d_scene(width=3200, height=2130, n_views=11, n_src=10, seed=3, jpeg=True, views=None) -> SyntheticScene:
+def make_eth3d_scene(width=3200, height=2130, n_views=11, n_src=10, seed=3, jpeg=True, views=None, workers=0) -> SyntheticScene:
     """Config 3: ETH3D-shaped indoor room, large weakly-textured walls plus textured furniture blocks."""
     f = 1800.0 * width / 3200.0
     K = _intrinsics(f, width, height)
@@ -312,10 +329,10 @@ def make_eth3d_scene(width=3200, height=2130, n_views=11, n_src=10, seed=3, jpeg
     for i in range(n_views):
         order = sorted((j for j in range(n_views) if j != i), key=lambda j: (abs(j - i), j))[:n_src]
         pairs[i] = [(j, float(100.0 / (1 + abs(j - i)))) for j in order]
-    return _finish("eth3d", width, height, faces, [K] * n_views, poses, pairs, jpeg, views)
+    return _finish("eth3d", width, height, faces, [K] * n_views, poses, pairs, jpeg, views, workers)
 
 
-def make_tnt_scene(width=1920, height=1080, n_views=300, n_src=10, seed=4, jpeg=True, views=None) -> SyntheticScene:
+def make_tnt_scene(width=1920, height=1080, n_views=300, n_src=10, seed=4, jpeg=True, views=None, workers=0) -> SyntheticScene:
     """Config 4: Tanks-and-Temples-shaped ring of views around textured blocks on a textured ground."""
     f = 1160.0 * width / 1920.0
     K = _intrinsics(f, width, height)
@@ -341,7 +358,7 @@ def make_tnt_scene(width=1920, height=1080, n_views=300, n_src=10, seed=4, jpeg=
             if len(cand) >= n_src:
                 break
         pairs[i] = cand[:n_src]
-    return _finish("tnt", width, height, faces, [K] * n_views, poses, pairs, jpeg, views)
+    return _finish("tnt", width, height, faces, [K] * n_views, poses, pairs, jpeg, views, workers)
 
 
 SCENES = {"plane": make_plane_scene, "dtu": make_dtu_scene, "eth3d": make_eth3d_scene, "tnt": make_tnt_scene}

@@ -1,0 +1,90 @@
+"""Shared definition of the small parity cases (used by tests/golden/make_golden.py, the CPU oracle tests and the
+GPU parity tests). Every case is a (scene, reference view) problem small enough for the CPU oracle to finish in seconds.
+
+Inputs are rendered by mpmvs_b200.synth (deterministic numpy); the golden files additionally store the uint8 images
+so the fixtures do not depend on the renderer staying bit-stable.
+"""
+import numpy as np
+
+from conftest import PKG, gt_planes_cam, problem_arrays
+
+SEED = 20240229
+
+
+def make_case(name):
+    synth = PKG.synth
+    if name == "plane3":      # config 1 shrunk: 3 views, textured tilted plane
+        sc = synth.make_plane_scene(width=96, height=64, n_views=3, seed=1, jpeg=False)
+        ref = 1
+    elif name == "dtu5":      # config 2 shrunk: 9-view grid, 4 sources, boxes on a table (occlusions, depth edges)
+        sc = synth.make_dtu_scene(width=128, height=96, grid=3, n_src=4, seed=2, jpeg=False)
+        ref = 4
+    elif name == "room6":     # config 3 shrunk: weak-texture room, 5 sources (planar prior case), odd height
+        sc = synth.make_eth3d_scene(width=120, height=81, n_views=6, n_src=5, seed=3, jpeg=False)
+        ref = 2
+    else:
+        raise KeyError(name)
+    ids, imgs, cams = problem_arrays(sc, ref)
+    return dict(name=name, scene=sc, ref=ref, ids=ids, images=imgs, cams=cams)
+
+
+CASES = ("plane3", "dtu5", "room6")
+
+
+def random_planes(case, seed=3):
+    """Camera-frame planes: GT normals/depths perturbed, so costs span the whole [0, 2] range."""
+    rng = np.random.default_rng(seed)
+    sc, ref = case["scene"], case["ref"]
+    pl = gt_planes_cam(sc, ref).astype(np.float64)
+    h, w = pl.shape[:2]
+    n = pl[..., :3] + rng.normal(0, 0.15, (h, w, 3))
+    n /= np.linalg.norm(n, axis=-1, keepdims=True)
+    cam = sc.cams[ref]
+    K = cam.K.astype(np.float64)
+    xs, ys = np.meshgrid(np.arange(w), np.arange(h))
+    X = np.stack([(xs - K[0, 2]) / K[0, 0], (ys - K[1, 2]) / K[1, 1], np.ones((h, w))], -1)
+    flip = (n * X).sum(-1) > 0
+    n[flip] *= -1
+    gt = sc.gt_depth[ref].astype(np.float64)
+    z = np.where(gt > 0, gt, 0.5 * (cam.depth_min + cam.depth_max)) * rng.uniform(0.97, 1.03, (h, w))
+    d = -(n * X * z[..., None]).sum(-1)
+    return np.concatenate([n, d[..., None]], -1).astype(np.float32)
+
+
+def src_depths(case, noise=0.0, seed=5):
+    """Source depth maps for the geometric-consistency pass: GT depth (0 where nothing was hit) + optional noise."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in case["ids"][1:]:
+        d = case["scene"].gt_depth[i].astype(np.float32).copy()
+        if noise:
+            d = (d * rng.uniform(1 - noise, 1 + noise, d.shape)).astype(np.float32)
+        out.append(d)
+    return out
+
+
+def prior_planes(case, seed=9):
+    """A per-pixel prior (GT plane, slightly off) and a triangle-id mask with holes (0 = no prior)."""
+    rng = np.random.default_rng(seed)
+    pl = gt_planes_cam(case["scene"], case["ref"]).copy()
+    pl[..., 3] *= rng.uniform(0.99, 1.01, pl.shape[:2]).astype(np.float32)
+    h, w = pl.shape[:2]
+    mask = (rng.integers(0, 7, (h // 8 + 1, w // 8 + 1)) > 1).astype(np.uint32)
+    mask = np.kron(mask, np.ones((8, 8), np.uint32))[:h, :w] * (1 + np.arange(h * w, dtype=np.uint32).reshape(h, w) // 64)
+    return pl, np.ascontiguousarray(mask)
+
+
+def world_state_from_gt(case, cost=0.3, noise=0.01, seed=11):
+    """(world normal, depth) planes + costs as a previous pass would have left them (geom restart input)."""
+    rng = np.random.default_rng(seed)
+    sc, ref = case["scene"], case["ref"]
+    gt = sc.gt_depth[ref].astype(np.float32)
+    cam = sc.cams[ref]
+    z = np.where(gt > 0, gt, 0.5 * (cam.depth_min + cam.depth_max)).astype(np.float32)
+    z = (z * rng.uniform(1 - noise, 1 + noise, z.shape)).astype(np.float32)
+    nw = sc.gt_normal[ref].astype(np.float32).copy()
+    bad = gt <= 0
+    nw[bad] = -(cam.R.astype(np.float32).T @ np.array([0, 0, 1], np.float32))
+    planes = np.concatenate([nw, z[..., None]], -1).astype(np.float32)
+    costs = rng.uniform(0.0, 2 * cost, z.shape).astype(np.float32)
+    return planes, costs
