@@ -14,13 +14,13 @@ SEED = 20240229
 def make_case(name):
     synth = PKG.synth
     if name == "plane3":      # config 1 shrunk: 3 views, textured tilted plane
-        sc = synth.make_plane_scene(width=96, height=64, n_views=3, seed=1, jpeg=False)
+        sc = synth.make_plane_scene(width=64, height=48, n_views=3, seed=1, jpeg=False)
         ref = 1
     elif name == "dtu5":      # config 2 shrunk: 9-view grid, 4 sources, boxes on a table (occlusions, depth edges)
-        sc = synth.make_dtu_scene(width=128, height=96, grid=3, n_src=4, seed=2, jpeg=False)
+        sc = synth.make_dtu_scene(width=96, height=72, grid=3, n_src=4, seed=2, jpeg=False)
         ref = 4
     elif name == "room6":     # config 3 shrunk: weak-texture room, 5 sources (planar prior case), odd height
-        sc = synth.make_eth3d_scene(width=120, height=81, n_views=6, n_src=5, seed=3, jpeg=False)
+        sc = synth.make_eth3d_scene(width=90, height=61, n_views=6, n_src=5, seed=3, jpeg=False)
         ref = 2
     else:
         raise KeyError(name)
@@ -88,3 +88,10 @@ def world_state_from_gt(case, cost=0.3, noise=0.01, seed=11):
     planes = np.concatenate([nw, z[..., None]], -1).astype(np.float32)
     costs = rng.uniform(0.0, 2 * cost, z.shape).astype(np.float32)
     return planes, costs
+
+
+def rng_hash(rng6):
+    """Per-pixel 32-bit digest of the 6-word XORWOW state (golden files store this instead of the full state)."""
+    r = np.asarray(rng6, dtype=np.uint32).astype(np.uint64)
+    k = np.array([0x9E3779B1, 0x85EBCA77, 0xC2B2AE3D, 0x27D4EB2F, 0x165667B1, 0xD3A2646C], dtype=np.uint64)
+    return ((r * k).sum(-1) & np.uint64(0xFFFFFFFF)).astype(np.uint32)

@@ -24,19 +24,19 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 from conftest import PKG  # noqa: E402,F401
-from cases import (CASES, SEED, make_case, prior_planes, random_planes, src_depths, world_state_from_gt)  # noqa: E402
+from cases import (CASES, SEED, make_case, rng_hash, prior_planes, random_planes, src_depths, world_state_from_gt)  # noqa: E402
 from conftest import gt_planes_cam  # noqa: E402
 import oracle_py  # noqa: E402
 
 STATE_KEYS = ("planes", "costs", "views", "rng", "geom")
-PIX = ((0, 0), (17, 5), (95, 63))
+PIX = ((0, 0), (17, 5), (63, 47))
 
 
 def put_state(out, prefix, st, geom=False):
     for k in STATE_KEYS:
         if k == "geom" and not geom:
             continue
-        out[f"{prefix}_{k}"] = st[k]
+        out[f"{prefix}_{k}"] = rng_hash(st[k]) if k == "rng" else st[k]
 
 
 def main():
