@@ -149,13 +149,16 @@ def run_ours(args, rank, world, local_rank, prob, barrier, allmax):
 
     torch.cuda.set_device(local_rank)
     W, H, n = prob["width"], prob["height"], len(prob["images"])
-    pm = capi.PatchMatch(device=local_rank)
+    fmt = {"f32": capi.TEX_F32, "f16": capi.TEX_F16, "u8": capi.TEX_U8}[args.tex]
+    pm = capi.PatchMatch(device=local_rank).set_tex_format(fmt)
     # resident arm: views uploaded once (the per-GPU image cache), runs leave results in HBM
     pm.set_problem(prob["images"], prob["cams"])
     pm.set_geom_consistency_params(False, False)
     pm.synchronize()
     # pinned host buffers for the e2e arm
-    pin_imgs = [torch.from_numpy(i).pin_memory() for i in prob["images"]]
+    # host images for the e2e arm: uint8 grey levels as decoded from the JPEGs when the storage is 8-bit, else float32
+    host_imgs = [i.astype(np.uint8) for i in prob["images"]] if args.tex == "u8" else prob["images"]
+    pin_imgs = [torch.from_numpy(i).pin_memory() for i in host_imgs]
     h_planes = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
     h_costs = torch.empty((H, W), dtype=torch.float32).pin_memory()
     pin_np = [t.numpy() for t in pin_imgs]
@@ -187,7 +190,7 @@ def run_ours(args, rank, world, local_rank, prob, barrier, allmax):
     tot_ms = allmax(tot_ms)
 
     # ---- timed region 2: end to end through the C ABI with host buffers
-    pm2 = capi.PatchMatch(device=local_rank)
+    pm2 = capi.PatchMatch(device=local_rank).set_tex_format(fmt)
     pm2.set_geom_consistency_params(False, False)
     for i in range(max(1, min(args.warmup, 2))):
         pm2.set_problem(pin_np, prob["cams"])
@@ -202,6 +205,7 @@ def run_ours(args, rank, world, local_rank, prob, barrier, allmax):
     e2e_s = allmax(time.time() - t0)   # host wall clock: includes H2D, launches, D2H and the final synchronisation
     barrier()
     checksum = float(h_costs.double().mean())
+    acc = synth.accuracy_at(h_planes.numpy()[..., 3], prob["gt_depth"])
 
     # ---- untimed: count executed NCC evaluations of one run (roofline numerator)
     pm.set_profiling(2)
@@ -228,9 +232,10 @@ def run_ours(args, rank, world, local_rank, prob, barrier, allmax):
         "ms_per_step": round(tot_ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": prob["label"], "width": W, "height": H, "src_views": nsrc, "passes": "photometric (scales 2,1,0 x 3 iterations)",
+                   "view_storage": args.tex, "lib_variant": os.environ.get("MPMVS_LIB_VARIANT", "default"),
                    "l2": "inputs_larger_than_l2 (11 float views = %.0f MB + %.0f MB state vs 126 MB L2)" % (n * W * H * 4 / 1e6, W * H * 56 / 1e6),
                    "parallelism": f"refs sharded over {world} gpu(s), no data-path collective in this pass"},
-        "e2e": {"value": round(e2e, 4), "unit": "Mpix/s", "h2d_bytes_per_step": int(n * W * H * 4 + 112 * n),
+        "e2e": {"value": round(e2e, 4), "unit": "Mpix/s", "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in pin_imgs) + 112 * n),
                 "d2h_bytes_per_step": int(W * H * 20), "ms_per_step": round(e2e_s * 1e3 / args.steps, 3)},
         "gpu_launches": int(launches),
         "kernel_ms_per_step": {"init": round(init_ms / args.steps, 3), "sweeps": round(sweep_ms / args.steps, 3),
@@ -242,7 +247,7 @@ def run_ours(args, rank, world, local_rank, prob, barrier, allmax):
                      "gtaps_per_s": round(taps_sweeps / sweep_s / 1e9, 2),
                      "hbm_peak_gbs": peaks.get("hbm_gbs")},
         "clocks": clocks,
-        "checksum_mean_cost": round(checksum, 6),
+        "checksum_mean_cost": round(checksum, 6), "accuracy_2_5_10cm": [round(a, 3) for a in acc],
         "wall_s_resident": round(wall_resident, 3),
     }
     pm.destroy(); pm2.destroy()
@@ -331,6 +336,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="eth3d")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tex", default="u8", choices=["f32", "f16", "u8"], help="storage format of the views in HBM")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 1)
 

@@ -18,6 +18,10 @@ import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libmpmvs_b200.so")
+# tuning experiments: tools/build_variants.py drops alternative builds of the same library next to the default one
+if os.environ.get("MPMVS_LIB_VARIANT"):
+    LIB_PATH = os.path.join(PKG_DIR, "variants", f"libmpmvs_b200_{os.environ['MPMVS_LIB_VARIANT']}.so")
+TEX_F32, TEX_F16, TEX_U8 = 0, 1, 2
 
 _lib = None
 
@@ -50,6 +54,9 @@ def lib() -> C.CDLL:
         "mpmvs_set_views": [vp, i, C.POINTER(vp), vp],
         "mpmvs_set_views_device": [vp, i, C.POINTER(vp), vp, vp],
         "mpmvs_cache_create": [i, i, i, i, C.POINTER(vp)],
+        "mpmvs_cache_create_fmt": [i, i, i, i, i, C.POINTER(vp)],
+        "mpmvs_set_views_u8": [vp, i, C.POINTER(vp), vp],
+        "mpmvs_set_tex_format": [vp, i],
         "mpmvs_cache_destroy": [vp],
         "mpmvs_cache_put": [vp, i, vp, i, i],
         "mpmvs_cache_put_u8": [vp, i, vp, i, i],
@@ -113,9 +120,9 @@ def _ptr(a):
 class ImageCache:
     """All images resident on one GPU in one layered texture (mpmvs_image_cache)."""
 
-    def __init__(self, device: int, width: int, height: int, capacity: int):
+    def __init__(self, device: int, width: int, height: int, capacity: int, tex_format: int = 0):
         self.h = C.c_void_p()
-        _ck(lib().mpmvs_cache_create(device, width, height, capacity, C.byref(self.h)), "cache_create")
+        _ck(lib().mpmvs_cache_create_fmt(device, width, height, capacity, tex_format, C.byref(self.h)), "cache_create")
 
     def put(self, image_id: int, img: np.ndarray):
         if img.dtype == np.uint8:
@@ -150,12 +157,21 @@ class PatchMatch:
         self._keep = []
 
     # ------------------------------------------------------------------ inputs
+    def set_tex_format(self, fmt: int):
+        _ck(lib().mpmvs_set_tex_format(self.h, int(fmt)), "set_tex_format")
+        return self
+
     def set_problem(self, images, cams_packed: np.ndarray):
-        imgs = [np.ascontiguousarray(i, dtype=np.float32) for i in images]
+        """images: float32 arrays (mpmvs_set_views) or uint8 arrays (mpmvs_set_views_u8), [0] = reference."""
+        u8 = all(i.dtype == np.uint8 for i in images)
+        imgs = [np.ascontiguousarray(i, dtype=np.uint8 if u8 else np.float32) for i in images]
         cams = np.ascontiguousarray(cams_packed)
         assert cams.itemsize == 112 and len(cams) == len(imgs)
         ptrs = (C.c_void_p * len(imgs))(*[i.ctypes.data for i in imgs])
-        _ck(lib().mpmvs_set_views(self.h, len(imgs), ptrs, cams.ctypes.data), "set_views")
+        if u8:
+            _ck(lib().mpmvs_set_views_u8(self.h, len(imgs), ptrs, cams.ctypes.data), "set_views_u8")
+        else:
+            _ck(lib().mpmvs_set_views(self.h, len(imgs), ptrs, cams.ctypes.data), "set_views")
         self.n = len(imgs)
         self.hgt, self.w = imgs[0].shape
         self._keep = [imgs, cams]

@@ -38,10 +38,12 @@ static_assert(sizeof(PmView) % 4 == 0, "PmView is staged word-wise");
 struct mpmvs_image_cache {
     int device = 0;
     int W = 0, H = 0, capacity = 0, used = 0;
+    int fmt = MPMVS_TEX_F32;
     cudaArray_t arr = nullptr;
     cudaTextureObject_t tex = 0;
     std::unordered_map<int, int> id2layer;
     std::vector<int> lw, lh;  // per-layer image size
+    void *stage_in = nullptr, *stage_out = nullptr;   // device staging for format conversion (W*H*4 bytes each)
 };
 
 struct mpmvs_problem {
@@ -53,6 +55,7 @@ struct mpmvs_problem {
     mpmvs_camera cams[MPMVS_MAX_VIEWS];
     mpmvs_image_cache* cache = nullptr;
     bool own_cache = false;
+    int tex_fmt = MPMVS_TEX_F32;       // storage format of the private cache (mpmvs_set_tex_format)
     int layers[MPMVS_MAX_VIEWS];
     // PatchMatchParams mirror (include/PatchMatch.h:48-67)
     int max_iterations = 3, top_k = 4, max_scale = 2;
@@ -95,6 +98,7 @@ PmFrame make_frame(const mpmvs_problem* p) {
     PmFrame F = pm_make_frame(p->cams[0], p->n, p->depth_min, p->depth_max, p->sigma_spatial, p->sigma_color, p->top_k,
                               p->geom, p->planar);
     F.ref_layer = p->layers[0];
+    F.tex_scale = p->cache->fmt == MPMVS_TEX_U8 ? 255.0f : 1.0f;
     int soft = 0;
     for (int i = 0; i < p->n; ++i)
         if (p->cams[i].width != p->cache->W || p->cams[i].height != p->cache->H) soft = 1;
@@ -103,8 +107,13 @@ PmFrame make_frame(const mpmvs_problem* p) {
     return F;
 }
 
-int cache_alloc(mpmvs_image_cache* c, int W, int H, int capacity) {
-    const cudaChannelFormatDesc desc = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+int cache_alloc(mpmvs_image_cache* c, int W, int H, int capacity, int fmt) {
+    cudaChannelFormatDesc desc;
+    if (fmt == MPMVS_TEX_F32) desc = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+    else if (fmt == MPMVS_TEX_F16) desc = cudaCreateChannelDescHalf();
+    else if (fmt == MPMVS_TEX_U8) desc = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
+    else return MPMVS_E_ARG;
+    c->fmt = fmt;
     CK(cudaMalloc3DArray(&c->arr, &desc, make_cudaExtent((size_t)W, (size_t)H, (size_t)capacity), cudaArrayLayered));
     cudaResourceDesc res;
     memset(&res, 0, sizeof(res));
@@ -118,7 +127,8 @@ int cache_alloc(mpmvs_image_cache* c, int W, int H, int capacity) {
     td.addressMode[1] = cudaAddressModeClamp;
     td.addressMode[2] = cudaAddressModeClamp;
     td.filterMode = cudaFilterModeLinear;
-    td.readMode = cudaReadModeElementType;
+    // 8-bit texels are fetched as UNORM floats (v/255, the only filterable integer read mode); the kernels scale by 255
+    td.readMode = fmt == MPMVS_TEX_U8 ? cudaReadModeNormalizedFloat : cudaReadModeElementType;
     td.normalizedCoords = 0;
     CK(cudaCreateTextureObject(&c->tex, &res, &td, nullptr));
     c->W = W; c->H = H; c->capacity = capacity; c->used = 0;
@@ -129,12 +139,17 @@ int cache_alloc(mpmvs_image_cache* c, int W, int H, int capacity) {
 }
 
 void cache_free(mpmvs_image_cache* c) {
+    cudaFree(c->stage_in); cudaFree(c->stage_out);
+    c->stage_in = c->stage_out = nullptr;
     if (c->tex) cudaDestroyTextureObject(c->tex);
     if (c->arr) cudaFreeArray(c->arr);
     c->tex = 0; c->arr = nullptr; c->capacity = c->used = 0;
     c->id2layer.clear();
 }
 
+size_t texel_bytes(int fmt) { return fmt == MPMVS_TEX_F32 ? 4 : (fmt == MPMVS_TEX_F16 ? 2 : 1); }
+
+// `src` holds texels already in the cache's storage format
 int cache_upload(mpmvs_image_cache* c, int layer, const void* src, size_t pitch, int w, int h, cudaMemcpyKind kind,
                  cudaStream_t st) {
     cudaMemcpy3DParms prm;
@@ -147,6 +162,28 @@ int cache_upload(mpmvs_image_cache* c, int layer, const void* src, size_t pitch,
     CK(cudaMemcpy3DAsync(&prm, st));
     c->lw[layer] = w; c->lh[layer] = h;
     return MPMVS_OK;
+}
+
+// Any grey image (float32 or uint8, host or device, pitched) into layer `layer`, converting to the cache's storage
+// format on the device when the two differ. All work is ordered on `st`.
+int cache_put_any(mpmvs_image_cache* c, int layer, const void* src, bool src_u8, size_t pitch, int w, int h, bool on_device,
+                  cudaStream_t st) {
+    const bool same = (src_u8 && c->fmt == MPMVS_TEX_U8) || (!src_u8 && c->fmt == MPMVS_TEX_F32);
+    if (same) return cache_upload(c, layer, src, pitch, w, h, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st);
+    if (!c->stage_in) {
+        CK(cudaMalloc(&c->stage_in, (size_t)c->W * c->H * 4));
+        CK(cudaMalloc(&c->stage_out, (size_t)c->W * c->H * 4));
+    }
+    const size_t elt = src_u8 ? 1 : 4;
+    const void* in = src;
+    size_t in_pitch = pitch;
+    if (!on_device) {
+        CK(cudaMemcpy2DAsync(c->stage_in, (size_t)w * elt, src, pitch, (size_t)w * elt, (size_t)h, cudaMemcpyHostToDevice, st));
+        in = c->stage_in;
+        in_pitch = (size_t)w * elt;
+    }
+    CK(pm_launch_convert(in, in_pitch, src_u8 ? 1 : 0, c->stage_out, c->fmt, w, h, st));
+    return cache_upload(c, layer, c->stage_out, (size_t)w * texel_bytes(c->fmt), w, h, cudaMemcpyDeviceToDevice, st);
 }
 
 int alloc_state(mpmvs_problem* p) {
@@ -218,7 +255,7 @@ int private_cache(mpmvs_problem* p, int n, const mpmvs_camera* cams) {
     int mw = 0, mh = 0;
     for (int i = 0; i < n; ++i) { mw = cams[i].width > mw ? cams[i].width : mw; mh = cams[i].height > mh ? cams[i].height : mh; }
     if (p->cache && !p->own_cache) p->cache = nullptr;
-    if (p->cache && (p->cache->W != mw || p->cache->H != mh || p->cache->capacity < n)) {
+    if (p->cache && (p->cache->W != mw || p->cache->H != mh || p->cache->capacity < n || p->cache->fmt != p->tex_fmt)) {
         cache_free(p->cache);
         delete p->cache;
         p->cache = nullptr;
@@ -228,7 +265,7 @@ int private_cache(mpmvs_problem* p, int n, const mpmvs_camera* cams) {
         if (!p->cache) return MPMVS_E_ARG;
         p->cache->device = p->device;
         p->own_cache = true;
-        int rc = cache_alloc(p->cache, mw, mh, n);
+        int rc = cache_alloc(p->cache, mw, mh, n, p->tex_fmt);
         if (rc) return rc;
     }
     for (int i = 0; i < n; ++i) p->layers[i] = i;
@@ -355,13 +392,17 @@ int mpmvs_destroy(mpmvs_problem* p) {
 
 // ---------------------------------------------------------------------------------------------- image cache
 int mpmvs_cache_create(int device, int max_width, int max_height, int capacity, mpmvs_image_cache** out) {
+    return mpmvs_cache_create_fmt(device, max_width, max_height, capacity, MPMVS_TEX_F32, out);
+}
+
+int mpmvs_cache_create_fmt(int device, int max_width, int max_height, int capacity, int tex_format, mpmvs_image_cache** out) {
     if (!out || max_width <= 0 || max_height <= 0 || capacity <= 0 || capacity > 2048) return MPMVS_E_ARG;
     int rc = ensure_device(device);
     if (rc) return rc;
     mpmvs_image_cache* c = new (std::nothrow) mpmvs_image_cache();
     if (!c) return MPMVS_E_ARG;
     c->device = device;
-    rc = cache_alloc(c, max_width, max_height, capacity);
+    rc = cache_alloc(c, max_width, max_height, capacity, tex_format);
     if (rc) { delete c; return rc; }
     *out = c;
     return MPMVS_OK;
@@ -385,55 +426,61 @@ static int cache_layer_for(mpmvs_image_cache* c, int image_id, int w, int h) {
     return layer;
 }
 
-int mpmvs_cache_put(mpmvs_image_cache* c, int image_id, const float* gray_host, int width, int height) {
+static int cache_put_host(mpmvs_image_cache* c, int image_id, const void* gray_host, bool u8, int width, int height) {
     if (!c || !gray_host) return MPMVS_E_ARG;
     CK(cudaSetDevice(c->device));
     const int layer = cache_layer_for(c, image_id, width, height);
     if (layer < 0) return MPMVS_E_ARG;
-    int rc = cache_upload(c, layer, gray_host, (size_t)width * sizeof(float), width, height, cudaMemcpyHostToDevice, 0);
+    int rc = cache_put_any(c, layer, gray_host, u8, (size_t)width * (u8 ? 1 : 4), width, height, false, 0);
     if (rc) return rc;
     CK(cudaStreamSynchronize(0));
     return MPMVS_OK;
 }
 
+int mpmvs_cache_put(mpmvs_image_cache* c, int image_id, const float* gray_host, int width, int height) {
+    return cache_put_host(c, image_id, gray_host, false, width, height);
+}
+
+// uint8 grey levels; in a float cache they become exactly what PatchMatchInit's convertTo(CV_32FC1) gives (PatchMatch.cpp:882)
 int mpmvs_cache_put_u8(mpmvs_image_cache* c, int image_id, const uint8_t* gray_host, int width, int height) {
-    if (!c || !gray_host) return MPMVS_E_ARG;
-    // uint8 -> float32 exactly as PatchMatchInit's convertTo(CV_32FC1) (PatchMatch.cpp:882)
-    std::vector<float> tmp((size_t)width * height);
-    for (size_t i = 0; i < tmp.size(); ++i) tmp[i] = (float)gray_host[i];
-    return mpmvs_cache_put(c, image_id, tmp.data(), width, height);
+    return cache_put_host(c, image_id, gray_host, true, width, height);
 }
 
 int mpmvs_cache_has(mpmvs_image_cache* c, int image_id) { return c && c->id2layer.count(image_id) ? 1 : 0; }
 
 // ---------------------------------------------------------------------------------------------- inputs
-int mpmvs_set_views(mpmvs_problem* p, int n, const float* const* gray_host, const mpmvs_camera* cams) {
-    int rc = check_views_args(p, n, gray_host, cams);
+static int set_views_any(mpmvs_problem* p, int n, const void* const* imgs, bool u8, const size_t* pitch_bytes, bool on_device,
+                         const mpmvs_camera* cams) {
+    int rc = check_views_args(p, n, imgs, cams);
     if (rc) return rc;
     CK(cudaSetDevice(p->device));
     rc = private_cache(p, n, cams);
     if (rc) return rc;
     for (int i = 0; i < n; ++i) {
-        rc = cache_upload(p->cache, i, gray_host[i], (size_t)cams[i].width * sizeof(float), cams[i].width, cams[i].height,
-                          cudaMemcpyHostToDevice, p->stream);
+        const size_t pitch = pitch_bytes ? pitch_bytes[i] : (size_t)cams[i].width * (u8 ? 1 : 4);
+        rc = cache_put_any(p->cache, i, imgs[i], u8, pitch, cams[i].width, cams[i].height, on_device, p->stream);
         if (rc) return rc;
     }
     return finish_views(p, n, cams);
 }
 
+int mpmvs_set_views(mpmvs_problem* p, int n, const float* const* gray_host, const mpmvs_camera* cams) {
+    return set_views_any(p, n, (const void* const*)gray_host, false, nullptr, false, cams);
+}
+
+int mpmvs_set_views_u8(mpmvs_problem* p, int n, const uint8_t* const* gray_host, const mpmvs_camera* cams) {
+    return set_views_any(p, n, (const void* const*)gray_host, true, nullptr, false, cams);
+}
+
 int mpmvs_set_views_device(mpmvs_problem* p, int n, const float* const* gray_dev, const size_t* pitch_bytes,
                            const mpmvs_camera* cams) {
-    int rc = check_views_args(p, n, gray_dev, cams);
-    if (rc) return rc;
-    CK(cudaSetDevice(p->device));
-    rc = private_cache(p, n, cams);
-    if (rc) return rc;
-    for (int i = 0; i < n; ++i) {
-        const size_t pitch = pitch_bytes ? pitch_bytes[i] : (size_t)cams[i].width * sizeof(float);
-        rc = cache_upload(p->cache, i, gray_dev[i], pitch, cams[i].width, cams[i].height, cudaMemcpyDeviceToDevice, p->stream);
-        if (rc) return rc;
-    }
-    return finish_views(p, n, cams);
+    return set_views_any(p, n, (const void* const*)gray_dev, false, pitch_bytes, true, cams);
+}
+
+int mpmvs_set_tex_format(mpmvs_problem* p, int tex_format) {
+    if (!p || tex_format < MPMVS_TEX_F32 || tex_format > MPMVS_TEX_U8) return MPMVS_E_ARG;
+    p->tex_fmt = tex_format;
+    return MPMVS_OK;
 }
 
 int mpmvs_set_views_cached(mpmvs_problem* p, mpmvs_image_cache* c, int n, const int* image_ids, const mpmvs_camera* cams) {

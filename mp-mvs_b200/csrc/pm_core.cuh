@@ -33,6 +33,15 @@
 #endif
 
 #define PM_MAX_SRC 32
+#ifndef PM_UNIFORM_VIEWS
+#define PM_UNIFORM_VIEWS 1   // profiles/r01_variant_sweep_*: 5-8 % faster once the cost table is in shared memory
+#endif
+#ifndef PM_VIEW_OUTER
+#define PM_VIEW_OUTER 0  // 1: the 8 propagation candidates are scored view by view (a source view's window stays in L1/TEX)
+#endif
+#ifndef PM_EARLY_OUT
+#define PM_EARLY_OUT 1   // stop scoring a refinement proposal once it can no longer be accepted (result-identical)
+#endif
 #define PM_PI_F 3.14159265358979323846f
 
 struct alignas(16) pm_f4 { float x, y, z, w; };
@@ -64,6 +73,7 @@ struct PmFrame {
     int W, H, nsrc, top_k;
     int geom, planar;
     int ref_layer;             // layer of the reference image
+    float tex_scale;           // 255 when the views are stored as 8-bit UNORM texels (fetch returns v/255), else 1
     int soft_clamp;            // 1 when the views differ in size: clamp-to-edge is then done on the coordinates
     unsigned long long tex;    // cudaTextureObject_t of the layered image array (one handle, warp-uniform:
                                // a per-view handle makes the compiler serialise every fetch per unique handle)
@@ -383,8 +393,15 @@ PM_HD void pm_region_offset(int r, int k, int& dx, int& dy) {
 // code stays small enough for the instruction cache; the decisions the reference takes between those
 // evaluations (view selection, candidate choice, proposal generation) sit at the top of iterations 8 and 9.
 // `ca` is the thread's private candidate cost table, 8 x nsrc floats (cost_array, cu:795).
-template <int SCALE, class Ctx>
-PM_HD void pm_sweep_pixel(const Ctx& c, const PmFrame& F, const PmState& S, int x, int y, int iter, float* ca) {
+// candidate cost table of one thread in thread-private memory (stride 1)
+struct PmTableLocal {
+    float* p; int nsrc;
+    PM_HD float& operator()(int r, int v) const { return p[r * nsrc + v]; }
+};
+
+// `ca` is any object with float& operator()(int region, int view): the thread's candidate cost table.
+template <int SCALE, class Ctx, class Table>
+PM_HD void pm_sweep_pixel(const Ctx& c, const PmFrame& F, const PmState& S, int x, int y, int iter, Table ca) {
     const int W = F.W, H = F.H, nsrc = F.nsrc;
     const int idx = y * W + x;
     PmRng rs = pm_rng_load(S.rng, idx);
@@ -412,8 +429,9 @@ PM_HD void pm_sweep_pixel(const Ctx& c, const PmFrame& F, const PmState& S, int 
     }
     // QUIRK cu:795: `float cost_array[8][32] = {2.0f}` -> element [0][0] is 2, everything else 0, and regions
     // without an in-bounds sample keep those values.
-    for (int k = 0; k < 8 * nsrc; ++k) ca[k] = 0.0f;
-    ca[0] = 2.0f;
+    for (int r = 0; r < 8; ++r)
+        for (int v = 0; v < nsrc; ++v) ca(r, v) = 0.0f;
+    ca(0, 0) = 2.0f;
 
     const float depth_sigma = (F.depth_max - F.depth_min) / 64.0f;
     const float two_ds2 = 2 * depth_sigma * depth_sigma;
@@ -433,8 +451,20 @@ PM_HD void pm_sweep_pixel(const Ctx& c, const PmFrame& F, const PmState& S, int 
     pm_f4 rand_n = cur, pert_n = cur, base_n = cur, prior_pl = cur;
     bool has_prior = false;
 
+#if PM_VIEW_OUTER
+    // Same 8 x nsrc evaluations as cu:798-819, ordered view-major: all candidates of one source view back to back.
 #pragma unroll 1
-    for (int h = 0; h < 14; ++h) {
+    for (int v = 0; v < nsrc; ++v) {
+#pragma unroll 1
+        for (int h = 0; h < 8; ++h) {
+            if (!((flags >> h) & 1u)) continue;
+            const PmHyp hyp = pm_hyp(F, S.planes[pos[h]], x, y);
+            ca(h, v) = pm_ncc<SCALE>(c, F, st, v, hyp, x, y, nexec);
+        }
+    }
+#endif
+#pragma unroll 1
+    for (int h = PM_VIEW_OUTER ? 8 : 0; h < 14; ++h) {
         if (h == 8) {
             // ---- view selection (cu:821-878)
             uint32_t nb[4];  // neighbour masks: up / down / left / right, gated by the flags of regions 0..3 (cu:824-830)
@@ -454,7 +484,7 @@ PM_HD void pm_sweep_pixel(const Ctx& c, const PmFrame& F, const PmState& S, int 
                 float count = 0.f, tmpw = 0.f; int count_false = 0;
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    const float cc = ca[r * nsrc + v];
+                    const float cc = ca(r, v);
                     if (cc < thr) { tmpw += pm_exp(cc * cc / (-0.18f)); count += 1.f; }
                     if (cc > 1.2f) ++count_false;
                 }
@@ -488,7 +518,7 @@ PM_HD void pm_sweep_pixel(const Ctx& c, const PmFrame& F, const PmState& S, int 
                 if (F.geom && fl) pl = S.planes[pos[r]];
                 for (uint32_t m = sel; m; m &= m - 1) {
                     const int v = pm_ffs(m) - 1;
-                    float term = ca[r * nsrc + v];
+                    float term = ca(r, v);
                     if (F.geom) term += fl ? 0.2f * pm_geom_cost(c, F, v, pl, x, y) : 0.1f * 3.0f;
                     acc += (float)vw.get(v) * term;
                 }
@@ -591,15 +621,27 @@ PM_HD void pm_sweep_pixel(const Ctx& c, const PmFrame& F, const PmState& S, int 
             tp = (i == 1 || i == 2) ? rand_n : (i == 3 ? pert_n : base_n);
             tp.w = pm_plane_distance(F, x, y, hd, tp);
             mask = sel;                             // cu:684-694
+#if PM_EARLY_OUT
+            // a proposal whose depth leaves the range is scored by the reference and then always rejected (cu:707,713)
+            const float dchk = pm_depth_from_plane(F, tp, x, y);
+            if (!(dchk >= F.depth_min && dchk <= F.depth_max)) continue;
+#endif
         }
         const PmHyp hyp = pm_hyp(F, tp, x, y);
         float tc = 0.f, tg = 0.f;
 #pragma unroll 1
+#if PM_UNIFORM_VIEWS
+        // every lane of a warp walks the views in the same order (lanes that do not need view v idle through it), so
+        // a warp-wide texture fetch stays inside one layer of the image array
+        for (int v = 0; v < nsrc; ++v) {
+            if (!((mask >> v) & 1u)) continue;
+#else
         for (uint32_t m = mask; m; m &= m - 1) {
             const int v = pm_ffs(m) - 1;
+#endif
             const float cst = pm_ncc<SCALE>(c, F, st, v, hyp, x, y, nexec);
             if (h < 8) {
-                ca[h * nsrc + v] = cst;
+                ca(h, v) = cst;
             } else {
                 const float wv = (float)vw.get(v);
                 if (F.geom) {
@@ -610,6 +652,11 @@ PM_HD void pm_sweep_pixel(const Ctx& c, const PmFrame& F, const PmState& S, int 
                 } else {
                     tc += wv * cst;
                 }
+#if PM_EARLY_OUT
+                // Costs are >= 0 and summed in the reference's order, so the running sum only grows: once it fails the
+                // acceptance test `tc / wnorm < cost_now` (cu:713) the remaining views cannot rescue the proposal.
+                if (h > 8 && !has_prior && !(tc / wnorm < cost_now)) break;
+#endif
             }
         }
         if (h == 8) {

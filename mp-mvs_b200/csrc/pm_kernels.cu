@@ -14,15 +14,28 @@
 // the per-view constants sit next to it. Source samples go through the texture unit: they are
 // homography-warped scattered bilinear reads, which is what the unit is built for, and it keeps the
 // reference's 9-bit-weight filtering bit-for-bit.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
+
+#include <type_traits>
 
 #include "pm_core.cuh"
 #include "pm_kernels.h"
 
 namespace {
 
-constexpr int BW = 32, BH = 8;
-constexpr int MIN_BLOCKS = 3;  // 3 x 256 threads per SM -> at most 85 registers per thread
+// Tuning knobs (compile-time; the defaults are what the B200 measurements in profiles/ selected).
+#ifndef PM_BH
+#define PM_BH 4            // thread rows per block: 32 x PM_BH threads (a 32 x 8 pixel tile of one checkerboard colour)
+#endif
+#ifndef PM_MIN_BLOCKS
+#define PM_MIN_BLOCKS 3    // resident blocks per SM the register allocation must allow
+#endif
+#ifndef PM_CA_SMEM
+#define PM_CA_SMEM 1       // 1: the 8 x nsrc candidate cost table lives in shared memory instead of local memory
+#endif
+constexpr int BW = 32, BH = PM_BH;
+constexpr int MIN_BLOCKS = PM_MIN_BLOCKS;
 
 template <int SCALE, int ROWS>
 struct Tile {
@@ -34,11 +47,18 @@ struct Tile {
     static constexpr int FLOATS = PITCH * TH;
 };
 
-template <int PITCH, bool SOFT_CLAMP>
+// candidate cost table of one thread in shared memory (stride = threads per block; PmTableLocal is the local-memory one)
+struct TableShared {
+    float* p; int nsrc;   // p already offset by the thread index; element k at p[k * threads]
+    __device__ __forceinline__ float& operator()(int r, int v) const { return p[(r * nsrc + v) * (BW * BH)]; }
+};
+
+template <int PITCH, bool SOFT_CLAMP, bool SCALED = false>
 struct DevCtx {
     const float* centre;   // shared-memory address of this thread's pixel inside the tile
     const PmView* views;   // shared memory
     cudaTextureObject_t tex;
+    float scale;           // texel value scale (255 for 8-bit UNORM storage); only read when SCALED
     __device__ __forceinline__ float ref(int dx, int dy) const { return centre[dy * PITCH + dx]; }
     __device__ __forceinline__ float src(int v, float xs, float ys) const {
         const PmView& V = views[v];
@@ -46,7 +66,8 @@ struct DevCtx {
             xs = fminf(fmaxf(xs, 0.5f), V.w - 0.5f);
             ys = fminf(fmaxf(ys, 0.5f), V.h - 0.5f);
         }
-        return tex2DLayered<float>(tex, xs, ys, V.layer);
+        const float t = tex2DLayered<float>(tex, xs, ys, V.layer);
+        return SCALED ? t * scale : t;
     }
     __device__ __forceinline__ float src_depth(int v, int xi, int yi) const {
         const PmView& V = views[v];
@@ -73,12 +94,15 @@ __device__ __forceinline__ void stage_tile(float* tile, PmView* sviews, const Pm
         const int ty = i / T::TW, tx = i - ty * T::TW;
         // exact texel fetch (weights 1/0 at texel centres); clamp-to-edge like the reference's texture (PatchMatch.cpp:1012-1018)
         const int gx = min(max(x0 - T::R + tx, 0), F.W - 1), gy = min(max(y0 - T::R + ty, 0), F.H - 1);
-        tile[ty * T::PITCH + tx] = tex2DLayered<float>((cudaTextureObject_t)F.tex, (float)gx + 0.5f, (float)gy + 0.5f, F.ref_layer);
+        const float t = tex2DLayered<float>((cudaTextureObject_t)F.tex, (float)gx + 0.5f, (float)gy + 0.5f, F.ref_layer);
+        // 8-bit UNORM storage returns v/255: v is recovered exactly by rounding (reference-side values stay bit-identical)
+        tile[ty * T::PITCH + tx] = F.tex_scale != 1.0f ? rintf(t * F.tex_scale) : t;
     }
     __syncthreads();
 }
 
-template <int SCALE, bool CL>
+// Variant = (window scale, soft clamp for mixed image sizes, scaled texel values)
+template <int SCALE, bool CL, bool SC>
 __global__ void __launch_bounds__(BW* BH, MIN_BLOCKS) pm_sweep_kernel(const PmFrame F, const PmState S, const PmView* gviews,
                                                            int red, int iter) {
     using T = Tile<SCALE, 2 * BH>;
@@ -90,15 +114,21 @@ __global__ void __launch_bounds__(BW* BH, MIN_BLOCKS) pm_sweep_kernel(const PmFr
     const int tx = threadIdx.x, ly = 2 * threadIdx.y + ((tx & 1) ^ red);
     const int x = x0 + tx, y = y0 + ly;
     if (x >= F.W || y >= F.H) return;
-    DevCtx<T::PITCH, CL> c;
+    DevCtx<T::PITCH, CL, SC> c;
     c.centre = tile + (ly + T::R) * T::PITCH + (tx + T::R);
     c.views = sviews;
     c.tex = (cudaTextureObject_t)F.tex;
+    c.scale = F.tex_scale;
+#if PM_CA_SMEM
+    float* cab = tile + T::FLOATS + threadIdx.y * BW + tx;
+    pm_sweep_pixel<SCALE>(c, F, S, x, y, iter, TableShared{cab, F.nsrc});
+#else
     float ca[8 * PM_MAX_SRC];
-    pm_sweep_pixel<SCALE>(c, F, S, x, y, iter, ca);
+    pm_sweep_pixel<SCALE>(c, F, S, x, y, iter, PmTableLocal{ca, F.nsrc});
+#endif
 }
 
-template <int SCALE, bool CL>
+template <int SCALE, bool CL, bool SC>
 __global__ void __launch_bounds__(BW* BH, MIN_BLOCKS) pm_init_kernel(const PmFrame F, const PmState S, const PmView* gviews,
                                                           unsigned long long seed) {
     using T = Tile<SCALE, BH>;
@@ -109,14 +139,15 @@ __global__ void __launch_bounds__(BW* BH, MIN_BLOCKS) pm_init_kernel(const PmFra
     stage_tile<SCALE, BH>(tile, sviews, gviews, F, x0, y0);
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     if (x >= F.W || y >= F.H) return;
-    DevCtx<T::PITCH, CL> c;
+    DevCtx<T::PITCH, CL, SC> c;
     c.centre = tile + (threadIdx.y + T::R) * T::PITCH + (threadIdx.x + T::R);
     c.views = sviews;
     c.tex = (cudaTextureObject_t)F.tex;
+    c.scale = F.tex_scale;
     pm_init_pixel<SCALE>(c, F, S, x, y, seed);
 }
 
-template <int SCALE, bool CL>
+template <int SCALE, bool CL, bool SC>
 __global__ void __launch_bounds__(BW* BH, MIN_BLOCKS) pm_ncc_map_kernel(const PmFrame F, const PmView* gviews,
                                                              const pm_f4* planes, float* out) {
     using T = Tile<SCALE, BH>;
@@ -127,10 +158,11 @@ __global__ void __launch_bounds__(BW* BH, MIN_BLOCKS) pm_ncc_map_kernel(const Pm
     stage_tile<SCALE, BH>(tile, sviews, gviews, F, x0, y0);
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     if (x >= F.W || y >= F.H) return;
-    DevCtx<T::PITCH, CL> c;
+    DevCtx<T::PITCH, CL, SC> c;
     c.centre = tile + (threadIdx.y + T::R) * T::PITCH + (threadIdx.x + T::R);
     c.views = sviews;
     c.tex = (cudaTextureObject_t)F.tex;
+    c.scale = F.tex_scale;
     const int idx = y * F.W + x;
     const PmRefStats st = pm_ref_stats<SCALE>(c, F);
     const PmHyp hyp = pm_hyp(F, planes[idx], x, y);
@@ -150,7 +182,7 @@ __global__ void __launch_bounds__(BW* BH) pm_geom_map_kernel(const PmFrame F, co
     }
     const int x = blockIdx.x * BW + threadIdx.x, y = blockIdx.y * BH + threadIdx.y;
     if (x >= F.W || y >= F.H) return;
-    DevCtx<1, false> c;
+    DevCtx<1, false, false> c;
     c.centre = nullptr;
     c.views = sviews;
     c.tex = (cudaTextureObject_t)F.tex;
@@ -179,6 +211,19 @@ __global__ void __launch_bounds__(256) pm_export_depth_kernel(const pm_f4* plane
     out[(size_t)y * pitch_f + x] = planes[y * W + x].w;
 }
 
+// grey image (float or 8-bit, pitched) -> texels in the storage format of the image cache (dense rows)
+template <class In, class Out>
+__global__ void __launch_bounds__(256) pm_convert_kernel(const unsigned char* in, size_t in_pitch, Out* out, int W, int H) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const float v = (float)reinterpret_cast<const In*>(in + (size_t)y * in_pitch)[x];
+    Out o;
+    if constexpr (std::is_same<Out, unsigned char>::value) o = (unsigned char)__float2uint_rn(fminf(fmaxf(v, 0.f), 255.f));
+    else if constexpr (std::is_same<Out, __half>::value) o = __float2half_rn(v);
+    else o = v;
+    out[(size_t)y * W + x] = o;
+}
+
 __global__ void pm_uniform_stream_kernel(unsigned long long seed, int x, int y, int n, float* out) {
     PmRng rs;
     pm_rng_init(rs, pm_mix_seed(seed, (uint32_t)x, (uint32_t)y));
@@ -189,39 +234,57 @@ template <int SCALE, int ROWS>
 constexpr size_t smem_bytes() {
     return PM_MAX_SRC * sizeof(PmView) + Tile<SCALE, ROWS>::FLOATS * sizeof(float);
 }
+inline size_t sweep_smem(size_t base, int nsrc) { return base + (PM_CA_SMEM ? (size_t)8 * nsrc * BW * BH * sizeof(float) : 0); }
 
 inline dim3 grid_full(int W, int H) { return dim3((W + BW - 1) / BW, (H + BH - 1) / BH, 1); }
 // Same row coverage as the reference's 32x16 blocks over H/2 rows (cu:1196): 16*ceil((H/2)/16) thread rows.
-inline dim3 grid_checker(int W, int H) { return dim3((W + BW - 1) / BW, 2 * (((H / 2) + 15) / 16), 1); }
+inline dim3 grid_checker(int W, int H) { return dim3((W + BW - 1) / BW, (16 / BH) * (((H / 2) + 15) / 16), 1); }
+
+// compile-time variant from the run-time (scale, soft_clamp, scaled) triple
+template <class Fn>
+inline cudaError_t dispatch(int scale, const PmFrame& F, Fn&& fn) {
+    const bool cl = F.soft_clamp != 0, sc = F.tex_scale != 1.0f;
+#define PM_CASE(S)                                                                  \
+    case S:                                                                         \
+        if (cl) { if (sc) fn(std::integral_constant<int, S>{}, std::true_type{}, std::true_type{});   \
+                  else fn(std::integral_constant<int, S>{}, std::true_type{}, std::false_type{}); }   \
+        else    { if (sc) fn(std::integral_constant<int, S>{}, std::false_type{}, std::true_type{});  \
+                  else fn(std::integral_constant<int, S>{}, std::false_type{}, std::false_type{}); }  \
+        break;
+    switch (scale) {
+        PM_CASE(0) PM_CASE(1) PM_CASE(2)
+        default: return cudaErrorInvalidValue;
+    }
+#undef PM_CASE
+    return cudaGetLastError();
+}
+
+template <class K>
+inline cudaError_t allow_smem(K kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
 
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------- launchers
 cudaError_t pm_launch_init(const PmFrame& F, const PmState& S, const PmView* gviews, unsigned long long seed, cudaStream_t st) {
-    if (F.soft_clamp) pm_init_kernel<2, true><<<grid_full(F.W, F.H), dim3(BW, BH), smem_bytes<2, BH>(), st>>>(F, S, gviews, seed);
-    else pm_init_kernel<2, false><<<grid_full(F.W, F.H), dim3(BW, BH), smem_bytes<2, BH>(), st>>>(F, S, gviews, seed);
-    return cudaGetLastError();
+    return dispatch(2, F, [&](auto s, auto cl, auto sc) {
+        pm_init_kernel<decltype(s)::value, decltype(cl)::value, decltype(sc)::value>
+            <<<grid_full(F.W, F.H), dim3(BW, BH), smem_bytes<decltype(s)::value, BH>(), st>>>(F, S, gviews, seed);
+    });
 }
 
 cudaError_t pm_launch_sweep(const PmFrame& F, const PmState& S, const PmView* gviews, int red, int iter, int scale,
                             cudaStream_t st) {
-    const dim3 g = grid_checker(F.W, F.H), b(BW, BH);
-    switch (scale) {
-        case 0:
-            if (F.soft_clamp) pm_sweep_kernel<0, true><<<g, b, smem_bytes<0, 2 * BH>(), st>>>(F, S, gviews, red, iter);
-            else pm_sweep_kernel<0, false><<<g, b, smem_bytes<0, 2 * BH>(), st>>>(F, S, gviews, red, iter);
-            break;
-        case 1:
-            if (F.soft_clamp) pm_sweep_kernel<1, true><<<g, b, smem_bytes<1, 2 * BH>(), st>>>(F, S, gviews, red, iter);
-            else pm_sweep_kernel<1, false><<<g, b, smem_bytes<1, 2 * BH>(), st>>>(F, S, gviews, red, iter);
-            break;
-        case 2:
-            if (F.soft_clamp) pm_sweep_kernel<2, true><<<g, b, smem_bytes<2, 2 * BH>(), st>>>(F, S, gviews, red, iter);
-            else pm_sweep_kernel<2, false><<<g, b, smem_bytes<2, 2 * BH>(), st>>>(F, S, gviews, red, iter);
-            break;
-        default: return cudaErrorInvalidValue;
-    }
-    return cudaGetLastError();
+    cudaError_t attr = cudaSuccess;
+    cudaError_t rc = dispatch(scale, F, [&](auto s, auto cl, auto sc) {
+        auto k = pm_sweep_kernel<decltype(s)::value, decltype(cl)::value, decltype(sc)::value>;
+        const size_t bytes = sweep_smem(smem_bytes<decltype(s)::value, 2 * BH>(), F.nsrc);
+        attr = allow_smem(k, bytes);
+        if (attr == cudaSuccess) k<<<grid_checker(F.W, F.H), dim3(BW, BH), bytes, st>>>(F, S, gviews, red, iter);
+    });
+    return attr != cudaSuccess ? attr : rc;
 }
 
 cudaError_t pm_launch_finalize(const PmFrame& F, const PmState& S, cudaStream_t st) {
@@ -233,27 +296,29 @@ cudaError_t pm_launch_finalize(const PmFrame& F, const PmState& S, cudaStream_t 
 
 cudaError_t pm_launch_ncc_map(const PmFrame& F, const PmView* gviews, const pm_f4* planes, int scale, float* out,
                               cudaStream_t st) {
-    const dim3 g = grid_full(F.W, F.H), b(BW, BH);
-    switch (scale) {
-        case 0:
-            if (F.soft_clamp) pm_ncc_map_kernel<0, true><<<g, b, smem_bytes<0, BH>(), st>>>(F, gviews, planes, out);
-            else pm_ncc_map_kernel<0, false><<<g, b, smem_bytes<0, BH>(), st>>>(F, gviews, planes, out);
-            break;
-        case 1:
-            if (F.soft_clamp) pm_ncc_map_kernel<1, true><<<g, b, smem_bytes<1, BH>(), st>>>(F, gviews, planes, out);
-            else pm_ncc_map_kernel<1, false><<<g, b, smem_bytes<1, BH>(), st>>>(F, gviews, planes, out);
-            break;
-        case 2:
-            if (F.soft_clamp) pm_ncc_map_kernel<2, true><<<g, b, smem_bytes<2, BH>(), st>>>(F, gviews, planes, out);
-            else pm_ncc_map_kernel<2, false><<<g, b, smem_bytes<2, BH>(), st>>>(F, gviews, planes, out);
-            break;
-        default: return cudaErrorInvalidValue;
-    }
-    return cudaGetLastError();
+    return dispatch(scale, F, [&](auto s, auto cl, auto sc) {
+        pm_ncc_map_kernel<decltype(s)::value, decltype(cl)::value, decltype(sc)::value>
+            <<<grid_full(F.W, F.H), dim3(BW, BH), smem_bytes<decltype(s)::value, BH>(), st>>>(F, gviews, planes, out);
+    });
 }
 
 cudaError_t pm_launch_geom_map(const PmFrame& F, const PmView* gviews, const pm_f4* planes, float* out, cudaStream_t st) {
     pm_geom_map_kernel<<<grid_full(F.W, F.H), dim3(BW, BH), 0, st>>>(F, gviews, planes, out);
+    return cudaGetLastError();
+}
+
+cudaError_t pm_launch_convert(const void* in, size_t in_pitch, int in_is_u8, void* out, int out_fmt, int W, int H, cudaStream_t st) {
+    const dim3 g((W + 31) / 32, (H + 7) / 8), b(32, 8);
+    const unsigned char* i = (const unsigned char*)in;
+    if (in_is_u8) {
+        if (out_fmt == 0) pm_convert_kernel<unsigned char, float><<<g, b, 0, st>>>(i, in_pitch, (float*)out, W, H);
+        else if (out_fmt == 1) pm_convert_kernel<unsigned char, __half><<<g, b, 0, st>>>(i, in_pitch, (__half*)out, W, H);
+        else pm_convert_kernel<unsigned char, unsigned char><<<g, b, 0, st>>>(i, in_pitch, (unsigned char*)out, W, H);
+    } else {
+        if (out_fmt == 0) pm_convert_kernel<float, float><<<g, b, 0, st>>>(i, in_pitch, (float*)out, W, H);
+        else if (out_fmt == 1) pm_convert_kernel<float, __half><<<g, b, 0, st>>>(i, in_pitch, (__half*)out, W, H);
+        else pm_convert_kernel<float, unsigned char><<<g, b, 0, st>>>(i, in_pitch, (unsigned char*)out, W, H);
+    }
     return cudaGetLastError();
 }
 

@@ -28,15 +28,15 @@ def has_gpu() -> bool:
         return False
 
 
-def build_emul() -> str:
-    """tests/emul/libpm_emul.so: host instantiation of the product's pm_core.cuh (debug aid, tests only)."""
+def build_emul(tag: str = "", flags=()) -> str:
+    """tests/emul/libpm_emul<tag>.so: host instantiation of the product's pm_core.cuh (debug aid, tests only)."""
     d = os.path.join(ROOT, "tests", "emul")
-    out = os.path.join(d, "libpm_emul.so")
+    out = os.path.join(d, f"libpm_emul{tag}.so")
     src = os.path.join(d, "pm_emul.cpp")
     deps = [src] + [os.path.join(ROOT, "mp-mvs_b200", "csrc", f) for f in ("pm_core.cuh", "pm_views.h")]
     if not os.path.exists(out) or any(os.path.getmtime(p) > os.path.getmtime(out) for p in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-ffp-contract=off",
-                               "-o", out, src])
+                               *flags, "-o", out, src])
     return out
 
 

@@ -79,7 +79,7 @@ void sweep(Emu* E, int red, int iter) {
             const int y = 2 * ty + ((x & 1) ^ (red ? 1 : 0));
             if (y >= E->H) continue;
             HostCtx c{E, x, y};
-            pm_sweep_pixel<SCALE>(c, F, S, x, y, iter, ca.data());
+            pm_sweep_pixel<SCALE>(c, F, S, x, y, iter, PmTableLocal{ca.data(), F.nsrc});
         }
 }
 void sweep_any(Emu* E, int red, int iter, int scale) {

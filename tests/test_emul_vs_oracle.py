@@ -130,3 +130,42 @@ def test_uniform_stream_is_xorwow(libs):
     c = libs.Oracle("cpu").uniform_stream(SEED, 4, 3, 256)
     assert not np.array_equal(a, c)       # (x, y) are hashed into the seed, not used as stream offsets
     assert abs(float(a.mean()) - 0.5) < 0.08
+
+
+def test_restructurings_are_bit_identical(libs):
+    """The kernel's tuning switches only reorder or skip work whose result cannot matter: early-out of refinement
+    proposals (PM_EARLY_OUT), view-major candidate scoring (PM_VIEW_OUTER), warp-uniform view order (PM_UNIFORM_VIEWS).
+    Whole runs must be bit-identical with every combination, in all three modes."""
+    import ctypes as C
+
+    from conftest import build_emul as be
+
+    variants = {"_plain": ["-DPM_EARLY_OUT=0"], "_eo": ["-DPM_EARLY_OUT=1"],
+                "_all": ["-DPM_EARLY_OUT=1", "-DPM_VIEW_OUTER=1", "-DPM_UNIFORM_VIEWS=1"]}
+    c = make_case("room6")
+    results = {}
+    for tag, flags in variants.items():
+        path = be(tag, flags)
+        libs.LIBS["emul" + tag] = (path, "emu_")
+        e = libs.Oracle("emul" + tag).set_problem(c["images"], c["cams"])
+        e.set_geom_consistency_params(False, False)
+        e.run(SEED)
+        out = [e.result()]
+        e.set_planar_prior_params()
+        e.set_geom_consistency_params(False, True)
+        e.set_prior(*prior_planes(c))
+        e.run(SEED + 1)
+        out.append(e.result())
+        e.destroy()
+        g = libs.Oracle("emul" + tag).set_problem(c["images"], c["cams"])
+        g.set_geom_consistency_params(True, False)
+        g.set_src_depths(src_depths(c, 0.002))
+        g.set_state(*world_state_from_gt(c))
+        g.run(SEED + 2)
+        out.append(g.result(geom=True))
+        g.destroy()
+        results[tag] = out
+    for tag in ("_eo", "_all"):
+        for a, b in zip(results["_plain"], results[tag]):
+            for x, y in zip(a, b):
+                np.testing.assert_array_equal(x, y)

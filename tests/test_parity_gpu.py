@@ -317,3 +317,36 @@ def test_error_paths(capi):
     with pytest.raises(capi.MpmvsError):
         pm.run(1)                                  # geom run without source depths
     pm.destroy()
+
+
+def test_u8_view_storage_matches_float_storage(capi, oracle, pkg):
+    """8-bit UNORM storage of the views (MPMVS_TEX_U8, the bench default) against float32 storage and the reference:
+    NCC maps agree to the same tolerance, whole runs meet the same agreement bar on config 1."""
+    c = make_case("dtu5")
+    rnd = random_planes(c)
+    a = capi.PatchMatch(0).set_tex_format(capi.TEX_F32).set_problem(c["images"], c["cams"])
+    b = capi.PatchMatch(0).set_tex_format(capi.TEX_U8).set_problem([i.astype(np.uint8) for i in c["images"]], c["cams"])
+    g = gold("dtu5")
+    for s in (0, 1, 2):
+        ma, mb = a.ncc_map(rnd, s), b.ncc_map(rnd, s)
+        check_cost_map("dtu5", mb, ma, frac=0.999)
+        check_cost_map("dtu5", mb, g[f"ncc_rnd_s{s}"])
+    a.destroy(); b.destroy()
+    need_ref(oracle)
+    synth = pkg.synth
+    sc = synth.make_plane_scene()
+    ids, imgs, cams = problem_arrays(sc, 1)
+    gt = sc.gt_depth[1]
+    pm = capi.PatchMatch(0).set_tex_format(capi.TEX_U8).set_problem([i.astype(np.uint8) for i in imgs], cams)
+    ref = oracle.Oracle("ref").set_problem(imgs, cams)
+    for o in (pm, ref):
+        o.set_geom_consistency_params(False, False)
+        o.run(1)
+    po, pr = pm.result(), ref.result()
+    valid = (gt > 0) & (pr[1] < 0.5)
+    ag = synth.depth_normal_agreement(po[0][..., 3], po[0][..., :3], pr[0][..., 3], pr[0][..., :3], valid)
+    print("u8 storage: same-seed agreement with the reference", ag)
+    assert ag >= 0.98
+    ao, ar = synth.accuracy_at(po[0][..., 3], gt), synth.accuracy_at(pr[0][..., 3], gt)
+    assert all(abs(x - y) <= 0.5 for x, y in zip(ao, ar))
+    pm.destroy(); ref.destroy()

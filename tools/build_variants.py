@@ -1,0 +1,36 @@
+"""Build tuning variants of libmpmvs_b200.so into mp-mvs_b200/variants/ (selected at run time with MPMVS_LIB_VARIANT)."""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "mp-mvs_b200", "csrc")
+OUT = os.path.join(ROOT, "mp-mvs_b200", "variants")
+BASE = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--use_fast_math", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
+
+# "default" = the in-tree defaults (PM_BH=4, PM_MIN_BLOCKS=3, PM_CA_SMEM=1, PM_UNIFORM_VIEWS=1, PM_EARLY_OUT=1)
+VARIANTS = {
+    "default": [],
+    "v1": ["-DPM_BH=8", "-DPM_MIN_BLOCKS=3", "-DPM_CA_SMEM=0", "-DPM_UNIFORM_VIEWS=0", "-DPM_EARLY_OUT=0"],   # first measured kernel
+    "noeo": ["-DPM_EARLY_OUT=0"],
+    "nouv": ["-DPM_UNIFORM_VIEWS=0"],
+    "local": ["-DPM_CA_SMEM=0", "-DPM_BH=8", "-DPM_MIN_BLOCKS=2"],
+    "mb2": ["-DPM_MIN_BLOCKS=2"],
+    "mb4": ["-DPM_MIN_BLOCKS=4"],
+}
+
+
+def build(name):
+    out = os.path.join(OUT, f"libmpmvs_b200_{name}.so")
+    cmd = ["/usr/local/cuda/bin/nvcc"] + BASE + VARIANTS[name] + ["-o", out, os.path.join(CSRC, "pm_kernels.cu"), os.path.join(CSRC, "pm_capi.cu")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return name, r.returncode, r.stderr[-400:]
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    names = sys.argv[1:] or list(VARIANTS)
+    with ThreadPoolExecutor(8) as ex:
+        for name, rc, err in ex.map(build, names):
+            print(name, "ok" if rc == 0 else "FAILED " + err)
