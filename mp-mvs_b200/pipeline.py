@@ -1,0 +1,253 @@
+"""Multi-GPU stage schedule of MP-MVS's depth estimation (main(), /root/reference/src/main.cpp:20-41), sharded by
+reference image: one process per GPU, `torch.distributed` for the plumbing, depth maps exchanged between passes with an
+all-gather over NVLink instead of through `depths.dmb` files (PatchMatch.cpp:620-633 writes, :934-950 reads).
+
+    stage 1   photometric Run() of every reference image            (main.cpp:20-26)
+    exchange  all-gather of the fresh depth maps (4 B/px per image)
+    stage 2   `geom_iterations` x { geometric-consistency Run(); exchange }   (main.cpp:29-41)
+
+Differences from the reference's schedule, both deliberate:
+  * Jacobi order: every image of pass k reads the depth maps of pass k-1 (the reference overwrites the files in place
+    image by image, so image i sees already-updated maps of images < i). Results are therefore identical for any number
+    of GPUs given the same seed;
+  * every reference image keeps its per-pixel state (planes, costs, view masks, RNG) resident in HBM between passes
+    (one `mpmvs_problem` per image), so a geom pass restarts from device memory, not from normals.dmb/costs.dmb.
+
+The compute engine is the CUDA library (CudaEngine -> capi.PatchMatch). The engine is injectable only so that the
+sharding/exchange logic can be exercised on CPU with the gloo backend by the tests; there is no CPU engine in the product.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+
+
+def shard_refs(ref_ids: Sequence[int], rank: int, world: int) -> List[int]:
+    """Contiguous blocks (rank r gets refs [r*B, (r+1)*B)), B = ceil(n / world): neighbouring images share sources,
+    so a rank's working set of views stays small. Equal image sizes -> equal cost per image."""
+    n = len(ref_ids)
+    b = (n + world - 1) // world
+    return list(ref_ids[rank * b:(rank + 1) * b])
+
+
+def block_size(n_refs: int, world: int) -> int:
+    return (n_refs + world - 1) // world
+
+
+def stage_seed(seed: int, ref_id: int, stage: int) -> int:
+    """Per (image, pass) seed, independent of the rank that runs it."""
+    z = (seed + 0x9E3779B97F4A7C15 * (ref_id * 64 + stage + 1)) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return z ^ (z >> 31)
+
+
+@dataclass
+class PipelineConfig:
+    geom_iterations: int = 2          # "Geometric consistency iterations"
+    max_src: int = 20                 # "Max source images num"
+    seed: int = 0
+    tex_format: int = 2               # capi.TEX_U8: views are 8-bit grey levels as decoded from the JPEGs
+    keep_normals: bool = True
+
+
+@dataclass
+class PassStats:
+    name: str
+    device_ms: float = 0.0           # sum of the Run() device times of this rank
+    exchange_ms: float = 0.0
+    n_refs: int = 0
+
+
+class CudaEngine:
+    """One reference image on one GPU: a resident `mpmvs_problem` (capi.PatchMatch)."""
+
+    def __init__(self, device: int, cache, ids: Sequence[int], cams_packed: np.ndarray):
+        from . import capi
+
+        self.pm = capi.PatchMatch(device)
+        self.pm.set_problem_cached(cache, list(ids), cams_packed)
+
+    def run_photometric(self, seed: int):
+        self.pm.reset_params()
+        self.pm.set_geom_consistency_params(False, False)
+        self.pm.run_async(seed)
+
+    def run_geometric(self, seed: int, src_depth_ptrs: Sequence[int]):
+        self.pm.set_geom_consistency_params(True, False)
+        self.pm.set_src_depths_device(list(src_depth_ptrs))
+        self.pm.run_async(seed)
+
+    def export_depth(self, dst_tensor):
+        self.pm.export_depth_device(dst_tensor.data_ptr(), dst_tensor.stride(0) * 4)
+
+    def device_ms(self) -> float:
+        return self.pm.last_run_ms()
+
+    def synchronize(self):
+        self.pm.synchronize()
+
+    def result(self):
+        import ctypes as C
+
+        from . import capi
+
+        planes = np.empty((self.pm.hgt, self.pm.w, 4), np.float32)
+        costs = np.empty((self.pm.hgt, self.pm.w), np.float32)
+        capi._ck(capi.lib().mpmvs_get_device_state(self.pm.h, planes.ctypes.data, costs.ctypes.data, None, None, None), "get_device_state")
+        return planes, costs
+
+    def destroy(self):
+        self.pm.destroy()
+
+
+class DensePipeline:
+    """entries: io_formats.SceneEntry list (pair.txt); cams: id -> io_formats.Camera; images: id -> uint8/float32 (H, W)."""
+
+    def __init__(self, entries, cams: Dict[int, object], images: Dict[int, np.ndarray], cfg: PipelineConfig, rank: int = 0,
+                 world: int = 1, device: int = 0, dist=None, engine_factory: Optional[Callable] = None, torch_device=None):
+        import torch
+
+        from . import io_formats
+
+        self.torch = torch
+        self.io = io_formats
+        self.cfg, self.rank, self.world, self.device, self.dist = cfg, rank, world, device, dist
+        self.entries = {e.ref_id: e for e in entries if e.estimate}
+        self.ref_ids = sorted(self.entries)
+        self.my_refs = shard_refs(self.ref_ids, rank, world)
+        self.block = block_size(len(self.ref_ids), world)
+        self.cams, self.images = cams, images
+        self.tdev = torch_device if torch_device is not None else torch.device("cuda", device)
+        self.engine_factory = engine_factory
+        self.engines: Dict[int, object] = {}
+        self.stats: List[PassStats] = []
+        any_cam = cams[self.ref_ids[0]]
+        self.H, self.W = int(any_cam.height), int(any_cam.width)
+        for i in self.ref_ids:
+            if (int(cams[i].height), int(cams[i].width)) != (self.H, self.W):
+                raise ValueError("the sharded pipeline requires equally sized views (one all-gather buffer)")
+        # slot of an image in the gathered buffer: rank-major, then position inside the rank's block
+        self.slot = {}
+        for r in range(world):
+            for k, ref in enumerate(shard_refs(self.ref_ids, r, world)):
+                self.slot[ref] = r * self.block + k
+        self.gathered = None          # [world * block, H, W] float32: depth maps of the previous pass
+        self.cache = None
+
+    # ------------------------------------------------------------------------------------------ set-up
+    def problem_ids(self, ref: int) -> List[int]:
+        ids = self.entries[ref].src_ids          # src_ids[0] == ref (GenerateSampleList, PatchMatch.cpp:84)
+        return [ids[0]] + list(ids[1:1 + self.cfg.max_src])
+
+    def setup(self):
+        need = sorted({i for ref in self.my_refs for i in self.problem_ids(ref)})
+        if self.engine_factory is None:
+            from . import capi
+
+            self.cache = capi.ImageCache(self.device, self.W, self.H, max(1, len(need)), self.cfg.tex_format)
+            for i in need:
+                self.cache.put(i, self.images[i])
+        for ref in self.my_refs:
+            ids = self.problem_ids(ref)
+            packed = self.io.pack_cameras([self.cams[i] for i in ids])
+            if self.engine_factory is None:
+                self.engines[ref] = CudaEngine(self.device, self.cache, ids, packed)
+            else:
+                self.engines[ref] = self.engine_factory(ids, [self.images[i] for i in ids], packed)
+        return len(need)
+
+    # ------------------------------------------------------------------------------------------ exchange
+    def _exchange(self, st: PassStats):
+        """All-gather of this pass's depth maps: rank r fills block r of a fresh [world*block, H, W] buffer."""
+        torch = self.torch
+        t0 = self._tick()
+        mine = torch.zeros((self.block, self.H, self.W), dtype=torch.float32, device=self.tdev)
+        self._sync_torch()             # the engines write on their own streams: the zero-fill must have landed
+        for k, ref in enumerate(self.my_refs):
+            self.engines[ref].export_depth(mine[k])
+        for ref in self.my_refs:
+            self.engines[ref].synchronize()
+        if self.world > 1:
+            out = torch.empty((self.world * self.block, self.H, self.W), dtype=torch.float32, device=self.tdev)
+            self.dist.all_gather_into_tensor(out, mine)
+            self._sync_torch()         # ... and the gathered maps must be complete before the engines' streams read them
+        else:
+            out = mine
+        self.gathered = out            # the previous buffer is dropped only now: Jacobi double buffering
+        st.exchange_ms = self._tock(t0)
+
+    def _sync_torch(self):
+        if self.tdev.type == "cuda":
+            self.torch.cuda.synchronize(self.tdev)
+
+    def _tick(self):
+        if self.tdev.type == "cuda":
+            e = self.torch.cuda.Event(enable_timing=True)
+            e.record()
+            return e
+        import time
+
+        return time.time()
+
+    def _tock(self, t0) -> float:
+        if self.tdev.type == "cuda":
+            e = self.torch.cuda.Event(enable_timing=True)
+            e.record()
+            e.synchronize()
+            return float(t0.elapsed_time(e))
+        import time
+
+        return (time.time() - t0) * 1e3
+
+    # ------------------------------------------------------------------------------------------ passes
+    def run(self):
+        if not self.engines:
+            self.setup()
+        st = PassStats("photometric", n_refs=len(self.my_refs))
+        for ref in self.my_refs:
+            self.engines[ref].run_photometric(stage_seed(self.cfg.seed, ref, 0))
+        for ref in self.my_refs:
+            self.engines[ref].synchronize()
+            st.device_ms += self.engines[ref].device_ms()
+        if self.cfg.geom_iterations > 0:
+            self._exchange(st)
+        self.stats.append(st)
+        for g in range(self.cfg.geom_iterations):
+            st = PassStats(f"geometric {g}", n_refs=len(self.my_refs))
+            prev = self.gathered
+            for ref in self.my_refs:
+                srcs = self.problem_ids(ref)[1:]
+                views = [prev[self.slot[i]] for i in srcs]
+                self.engines[ref].run_geometric(stage_seed(self.cfg.seed, ref, 1 + g), [v.data_ptr() for v in views] if self.tdev.type == "cuda" else views)
+            for ref in self.my_refs:
+                self.engines[ref].synchronize()
+                st.device_ms += self.engines[ref].device_ms()
+            if g + 1 < self.cfg.geom_iterations:
+                self._exchange(st)
+            self.stats.append(st)
+        return self.stats
+
+    def results(self) -> Dict[int, tuple]:
+        return {ref: self.engines[ref].result() for ref in self.my_refs}
+
+    def write_results(self, out_folder: str):
+        """<out>/MPMVS/2333_%08d/{depths,normals,costs}.dmb (PatchMatch.cpp:510-513,620-633)."""
+        import os
+
+        for ref, (planes, costs) in self.results().items():
+            d = self.io.result_dir(out_folder, ref)
+            os.makedirs(d, exist_ok=True)
+            self.io.write_dmb(os.path.join(d, "depths.dmb"), np.ascontiguousarray(planes[..., 3]))
+            self.io.write_dmb(os.path.join(d, "normals.dmb"), np.ascontiguousarray(planes[..., :3]))
+            self.io.write_dmb(os.path.join(d, "costs.dmb"), costs)
+
+    def destroy(self):
+        for e in self.engines.values():
+            e.destroy()
+        self.engines.clear()
+        if self.cache is not None:
+            self.cache.destroy()
+            self.cache = None
