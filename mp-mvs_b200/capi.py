@@ -93,6 +93,11 @@ def lib() -> C.CDLL:
         "mpmvs_ncc_map": [vp, vp, i, vp],
         "mpmvs_geom_map": [vp, vp, vp],
         "mpmvs_uniform_stream": [u64, i, i, i, vp],
+        "mpmvs_delaunay": [vp, i, i, i, vp, i, C.POINTER(i)],
+        "mpmvs_build_prior": [vp, vp],
+        "mpmvs_pick_vertices": [vp, i, vp, i, C.POINTER(i)],
+        "mpmvs_prior_from_triangles": [vp, vp, i, vp, i, C.POINTER(i)],
+        "mpmvs_get_prior": [vp, vp, vp],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -105,7 +110,9 @@ def lib() -> C.CDLL:
     return L
 
 
-EXPORTED = None  # filled by tests from include/mpmvs_b200.h
+class PriorStats(C.Structure):
+    _fields_ = [("n_vertices", C.c_int), ("n_triangles", C.c_int), ("n_prior_pixels", C.c_int), ("pick_ms", C.c_float),
+                ("delaunay_ms", C.c_float), ("raster_ms", C.c_float), ("total_ms", C.c_float)]
 
 
 def _ck(rc: int, what: str):
@@ -115,6 +122,15 @@ def _ck(rc: int, what: str):
 
 def _ptr(a):
     return None if a is None else a.ctypes.data
+
+
+def delaunay(xy: np.ndarray, width: int, height: int) -> np.ndarray:
+    """Delaunay triangulation of integer pixel positions (n, 2) -> (m, 3) vertex indices (host code, no GPU needed)."""
+    pts = np.ascontiguousarray(xy, dtype=np.int32).reshape(-1, 2)
+    out = np.empty((2 * len(pts) + 4, 3), np.int32)
+    n = C.c_int()
+    _ck(lib().mpmvs_delaunay(pts.ctypes.data, len(pts), width, height, out.ctypes.data, len(out), C.byref(n)), "delaunay")
+    return out[: n.value].copy()
 
 
 class ImageCache:
@@ -252,6 +268,33 @@ class PatchMatch:
         n = C.c_int()
         _ck(lib().mpmvs_last_run_launches(self.h, C.byref(n)), "last_run_launches")
         return int(n.value)
+
+    # ------------------------------------------------------------------ planar-prior stage
+    def build_prior(self) -> dict:
+        """Vertex picking + Delaunay + rasterisation + plane fit on the state of the previous run (mpmvs_build_prior)."""
+        st = PriorStats()
+        _ck(lib().mpmvs_build_prior(self.h, C.byref(st)), "build_prior")
+        return {k: getattr(st, k) for k, _ in PriorStats._fields_}
+
+    def pick_vertices(self, geom_variant: bool = False) -> np.ndarray:
+        cap = 3 * ((self.w + 4) // 5) * ((self.hgt + 4) // 5)
+        out = np.empty((cap, 2), np.int32)
+        n = C.c_int()
+        _ck(lib().mpmvs_pick_vertices(self.h, int(geom_variant), out.ctypes.data, cap, C.byref(n)), "pick_vertices")
+        return out[: n.value].copy()
+
+    def prior_from_triangles(self, xy: np.ndarray, tris: np.ndarray) -> int:
+        xy = np.ascontiguousarray(xy, dtype=np.int32).reshape(-1, 2)
+        tris = np.ascontiguousarray(tris, dtype=np.int32).reshape(-1, 3)
+        n = C.c_int()
+        _ck(lib().mpmvs_prior_from_triangles(self.h, xy.ctypes.data, len(xy), tris.ctypes.data, len(tris), C.byref(n)), "prior_from_triangles")
+        return int(n.value)
+
+    def get_prior(self):
+        prior = np.empty((self.hgt, self.w, 4), np.float32)
+        mask = np.empty((self.hgt, self.w), np.uint32)
+        _ck(lib().mpmvs_get_prior(self.h, prior.ctypes.data, mask.ctypes.data), "get_prior")
+        return prior, mask
 
     def set_profiling(self, flags: int):
         _ck(lib().mpmvs_set_profiling(self.h, int(flags)), "set_profiling")

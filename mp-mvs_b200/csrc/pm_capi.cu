@@ -14,6 +14,7 @@
 // There is no CPU fallback: without a CUDA device every entry point fails with MPMVS_E_NO_DEVICE.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -23,6 +24,7 @@
 
 #include "../../include/mpmvs_b200.h"
 #include "pm_core.cuh"
+#include "pm_delaunay.h"
 #include "pm_kernels.h"
 #include "pm_views.h"
 
@@ -82,6 +84,11 @@ struct mpmvs_problem {
     std::vector<cudaEvent_t> pev;          // pev[0] before init, pev[1] after init, pev[2+k] after sweep k, last after finalize
     int pev_used = 0;
     unsigned long long* d_counters = nullptr;
+    // planar-prior stage scratch (mpmvs_build_prior)
+    short2* d_cell_xy = nullptr; unsigned char* d_cell_n = nullptr; size_t cells_cap = 0;
+    int2* d_vxy = nullptr; int3* d_tris = nullptr; pm_f4* d_tri_planes = nullptr; size_t vtx_cap = 0, tri_cap = 0;
+    unsigned int* d_prior_count = nullptr;
+    std::vector<short> h_cell_xy; std::vector<unsigned char> h_cell_n;
 };
 
 namespace {
@@ -385,6 +392,8 @@ int mpmvs_destroy(mpmvs_problem* p) {
     cudaEventDestroy(p->ev1);
     for (cudaEvent_t e : p->pev) cudaEventDestroy(e);
     cudaFree(p->d_counters);
+    cudaFree(p->d_cell_xy); cudaFree(p->d_cell_n); cudaFree(p->d_vxy); cudaFree(p->d_tris); cudaFree(p->d_tri_planes);
+    cudaFree(p->d_prior_count);
     if (p->own_stream) cudaStreamDestroy(p->stream);
     delete p;
     return MPMVS_OK;
@@ -788,6 +797,118 @@ int mpmvs_geom_map(mpmvs_problem* p, const float* planes4_host, float* out_host)
     cudaFree(dp);
     cudaFree(dout);
     return (int)e;
+}
+
+// ---------------------------------------------------------------------------------------------- planar-prior host stage
+int mpmvs_delaunay(const int* xy, int n, int width, int height, int* tris_out, int max_tris, int* n_tris) {
+    if (!xy || n < 0 || width <= 0 || height <= 0 || !n_tris) return MPMVS_E_ARG;
+    for (int i = 0; i < n; ++i)
+        if (xy[2 * i] < 0 || xy[2 * i] >= width || xy[2 * i + 1] < 0 || xy[2 * i + 1] >= height) return MPMVS_E_ARG;
+    pmd::Delaunay d(xy, n, width, height);
+    std::vector<int> t;
+    d.triangles(t);
+    *n_tris = (int)(t.size() / 3);
+    if (tris_out) {
+        if ((int)(t.size() / 3) > max_tris) return MPMVS_E_ARG;
+        memcpy(tris_out, t.data(), t.size() * sizeof(int));
+    }
+    return MPMVS_OK;
+}
+
+int mpmvs_pick_vertices(mpmvs_problem* p, int geom_variant, int* xy_out, int max_vertices, int* n_out) {
+    if (!p || p->n < 2 || !n_out) return MPMVS_E_ARG;
+    CK(cudaSetDevice(p->device));
+    const int cx = (p->W + 4) / 5, cy = (p->H + 4) / 5;
+    const size_t cells = (size_t)cx * cy;
+    if (cells > p->cells_cap) {
+        cudaFree(p->d_cell_xy); cudaFree(p->d_cell_n);
+        p->d_cell_xy = nullptr; p->d_cell_n = nullptr; p->cells_cap = 0;
+        CK(cudaMalloc((void**)&p->d_cell_xy, cells * 3 * sizeof(short2)));
+        CK(cudaMalloc((void**)&p->d_cell_n, cells));
+        p->cells_cap = cells;
+    }
+    p->h_cell_xy.resize(cells * 6);
+    p->h_cell_n.resize(cells);
+    CK(pm_launch_pick_vertices(p->S.costs, p->S.geom, p->W, p->H, geom_variant ? 1 : 0, p->d_cell_xy, p->d_cell_n, p->stream));
+    CK(cudaMemcpyAsync(p->h_cell_xy.data(), p->d_cell_xy, cells * 3 * sizeof(short2), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(p->h_cell_n.data(), p->d_cell_n, cells, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    int n = 0;
+    for (size_t c = 0; c < cells; ++c)      // row-major cells, the order GetTriangulateVertices pushes them (PatchMatch.cpp:788-851)
+        for (int k = 0; k < p->h_cell_n[c]; ++k) {
+            if (xy_out) {
+                if (n >= max_vertices) return MPMVS_E_ARG;
+                xy_out[2 * n] = p->h_cell_xy[(c * 3 + k) * 2];
+                xy_out[2 * n + 1] = p->h_cell_xy[(c * 3 + k) * 2 + 1];
+            }
+            ++n;
+        }
+    *n_out = n;
+    return MPMVS_OK;
+}
+
+int mpmvs_prior_from_triangles(mpmvs_problem* p, const int* xy, int n_vertices, const int* tris, int n_tris, int* n_prior_pixels) {
+    if (!p || p->n < 2 || n_vertices < 0 || n_tris < 0 || (n_tris > 0 && (!xy || !tris))) return MPMVS_E_ARG;
+    CK(cudaSetDevice(p->device));
+    if ((size_t)n_vertices > p->vtx_cap) {
+        cudaFree(p->d_vxy); p->d_vxy = nullptr; p->vtx_cap = 0;
+        CK(cudaMalloc((void**)&p->d_vxy, sizeof(int2) * (size_t)n_vertices));
+        p->vtx_cap = (size_t)n_vertices;
+    }
+    if ((size_t)n_tris > p->tri_cap) {
+        cudaFree(p->d_tris); cudaFree(p->d_tri_planes); p->d_tris = nullptr; p->d_tri_planes = nullptr; p->tri_cap = 0;
+        CK(cudaMalloc((void**)&p->d_tris, sizeof(int3) * (size_t)n_tris));
+        CK(cudaMalloc((void**)&p->d_tri_planes, sizeof(pm_f4) * (size_t)n_tris));
+        p->tri_cap = (size_t)n_tris;
+    }
+    if (!p->d_prior_count) CK(cudaMalloc((void**)&p->d_prior_count, sizeof(unsigned int)));
+    if (n_vertices) CK(cudaMemcpyAsync(p->d_vxy, xy, sizeof(int2) * (size_t)n_vertices, cudaMemcpyHostToDevice, p->stream));
+    if (n_tris) CK(cudaMemcpyAsync(p->d_tris, tris, sizeof(int3) * (size_t)n_tris, cudaMemcpyHostToDevice, p->stream));
+    CK(pm_launch_prior(make_frame(p), p->S.planes, p->d_vxy, p->d_tris, n_tris, p->d_tri_planes, p->d_mask, p->d_prior, p->d_prior_count,
+                       p->stream));
+    unsigned int count = 0;
+    CK(cudaMemcpyAsync(&count, p->d_prior_count, sizeof(count), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    if (n_prior_pixels) *n_prior_pixels = (int)count;
+    p->has_prior = true;
+    return MPMVS_OK;
+}
+
+int mpmvs_build_prior(mpmvs_problem* p, mpmvs_prior_stats* stats) {
+    if (!p || p->n < 2 || !p->ran) return MPMVS_E_ARG;
+    using clk = std::chrono::steady_clock;
+    auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<float, std::milli>(b - a).count(); };
+    const auto t0 = clk::now();
+    const int max_v = 3 * ((p->W + 4) / 5) * ((p->H + 4) / 5);
+    std::vector<int> xy((size_t)2 * max_v);
+    int nv = 0;
+    int rc = mpmvs_pick_vertices(p, p->geomPlanarPrior ? 1 : 0, xy.data(), max_v, &nv);
+    if (rc) return rc;
+    const auto t1 = clk::now();
+    std::vector<int> tris;
+    if (nv >= 3) {
+        pmd::Delaunay d(xy.data(), nv, p->W, p->H);
+        d.triangles(tris);
+    }
+    const auto t2 = clk::now();
+    int npx = 0;
+    rc = mpmvs_prior_from_triangles(p, xy.data(), nv, tris.data(), (int)(tris.size() / 3), &npx);
+    if (rc) return rc;
+    const auto t3 = clk::now();
+    if (stats) {
+        stats->n_vertices = nv; stats->n_triangles = (int)(tris.size() / 3); stats->n_prior_pixels = npx;
+        stats->pick_ms = ms(t0, t1); stats->delaunay_ms = ms(t1, t2); stats->raster_ms = ms(t2, t3); stats->total_ms = ms(t0, t3);
+    }
+    return MPMVS_OK;
+}
+
+int mpmvs_get_prior(mpmvs_problem* p, float* prior_planes4_host, uint32_t* mask_host) {
+    if (!p || p->n < 2 || !p->has_prior) return MPMVS_E_ARG;
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->stream));
+    if (prior_planes4_host) CK(cudaMemcpy(prior_planes4_host, p->d_prior, p->wh * sizeof(pm_f4), cudaMemcpyDeviceToHost));
+    if (mask_host) CK(cudaMemcpy(mask_host, p->d_mask, p->wh * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return MPMVS_OK;
 }
 
 int mpmvs_uniform_stream(uint64_t seed, int x, int y, int n, float* out_host) {

@@ -16,4 +16,9 @@ cudaError_t pm_launch_geom_map(const PmFrame& F, const PmView* gviews, const pm_
 cudaError_t pm_launch_convert(const void* in, size_t in_pitch, int in_is_u8, void* out, int out_fmt, int W, int H, cudaStream_t st);
 cudaError_t pm_launch_export_depth(const pm_f4* planes, float* out, int W, int H, int pitch_floats, cudaStream_t st);
 cudaError_t pm_launch_uniform_stream(unsigned long long seed, int x, int y, int n, float* out, cudaStream_t st);
+// planar-prior stage (pm_prior.cu)
+cudaError_t pm_launch_pick_vertices(const float* costs, const float* geom, int W, int H, int geom_variant, short2* out_xy,
+                                    unsigned char* out_n, cudaStream_t st);
+cudaError_t pm_launch_prior(const PmFrame& F, const pm_f4* planes, const int2* vxy, const int3* tris, int n_tris, pm_f4* tri_planes,
+                            unsigned int* mask, pm_f4* prior, unsigned int* count, cudaStream_t st);
 #endif

@@ -18,12 +18,17 @@ VARIANTS = {
     "local": ["-DPM_CA_SMEM=0", "-DPM_BH=8", "-DPM_MIN_BLOCKS=2"],
     "mb2": ["-DPM_MIN_BLOCKS=2"],
     "mb4": ["-DPM_MIN_BLOCKS=4"],
+    "mb5": ["-DPM_MIN_BLOCKS=5"],
+    "bh2mb6": ["-DPM_BH=2", "-DPM_MIN_BLOCKS=6"],
+    "bh2mb8": ["-DPM_BH=2", "-DPM_MIN_BLOCKS=8"],
+    "bh8mb2": ["-DPM_BH=8", "-DPM_MIN_BLOCKS=2"],
+    "bh8mb1": ["-DPM_BH=8", "-DPM_MIN_BLOCKS=1"],
 }
 
 
 def build(name):
     out = os.path.join(OUT, f"libmpmvs_b200_{name}.so")
-    cmd = ["/usr/local/cuda/bin/nvcc"] + BASE + VARIANTS[name] + ["-o", out, os.path.join(CSRC, "pm_kernels.cu"), os.path.join(CSRC, "pm_capi.cu")]
+    cmd = ["/usr/local/cuda/bin/nvcc"] + BASE + VARIANTS[name] + ["-o", out, os.path.join(CSRC, "pm_kernels.cu"), os.path.join(CSRC, "pm_prior.cu"), os.path.join(CSRC, "pm_capi.cu")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     return name, r.returncode, r.stderr[-400:]
 
