@@ -73,6 +73,7 @@ def lib() -> C.CDLL:
         "mpmvs_run_async": [vp, u64],
         "mpmvs_run_into": [vp, u64, vp, vp, vp],
         "mpmvs_synchronize": [vp],
+        "mpmvs_get_results_async": [vp, vp, vp, vp],
         "mpmvs_last_run_ms": [vp, fp],
         "mpmvs_last_run_launches": [vp, C.POINTER(i)],
         "mpmvs_set_profiling": [vp, i],
@@ -98,6 +99,7 @@ def lib() -> C.CDLL:
         "mpmvs_pick_vertices": [vp, i, vp, i, C.POINTER(i)],
         "mpmvs_prior_from_triangles": [vp, vp, i, vp, i, C.POINTER(i)],
         "mpmvs_get_prior": [vp, vp, vp],
+        "mpmvs_get_prior_pixels": [vp, C.POINTER(i)],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -259,6 +261,10 @@ class PatchMatch:
     def synchronize(self):
         _ck(lib().mpmvs_synchronize(self.h), "synchronize")
 
+    def get_results_async(self, planes=None, costs=None, geom=None):
+        """Enqueue D2H copies into (pinned) numpy arrays; synchronize() before reading them."""
+        _ck(lib().mpmvs_get_results_async(self.h, _ptr(planes), _ptr(costs), _ptr(geom)), "get_results_async")
+
     def last_run_ms(self) -> float:
         ms = C.c_float()
         _ck(lib().mpmvs_last_run_ms(self.h, C.byref(ms)), "last_run_ms")
@@ -288,6 +294,11 @@ class PatchMatch:
         tris = np.ascontiguousarray(tris, dtype=np.int32).reshape(-1, 3)
         n = C.c_int()
         _ck(lib().mpmvs_prior_from_triangles(self.h, xy.ctypes.data, len(xy), tris.ctypes.data, len(tris), C.byref(n)), "prior_from_triangles")
+        return int(n.value)
+
+    def prior_pixels(self) -> int:
+        n = C.c_int()
+        _ck(lib().mpmvs_get_prior_pixels(self.h, C.byref(n)), "get_prior_pixels")
         return int(n.value)
 
     def get_prior(self):

@@ -606,6 +606,15 @@ int mpmvs_run_into(mpmvs_problem* p, uint64_t seed, float* planes4_host, float* 
     return MPMVS_OK;
 }
 
+int mpmvs_get_results_async(mpmvs_problem* p, float* planes4_host, float* costs_host, float* geom_costs_host) {
+    if (!p || p->n < 2) return MPMVS_E_ARG;
+    CK(cudaSetDevice(p->device));
+    if (planes4_host) CK(cudaMemcpyAsync(planes4_host, p->S.planes, p->wh * sizeof(pm_f4), cudaMemcpyDeviceToHost, p->stream));
+    if (costs_host) CK(cudaMemcpyAsync(costs_host, p->S.costs, p->wh * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    if (geom_costs_host) CK(cudaMemcpyAsync(geom_costs_host, p->S.geom, p->wh * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    return MPMVS_OK;
+}
+
 int mpmvs_run(mpmvs_problem* p, uint64_t seed) {
     if (!p) return MPMVS_E_ARG;
     int rc = ensure_mirrors(p);
@@ -866,11 +875,20 @@ int mpmvs_prior_from_triangles(mpmvs_problem* p, const int* xy, int n_vertices, 
     if (n_tris) CK(cudaMemcpyAsync(p->d_tris, tris, sizeof(int3) * (size_t)n_tris, cudaMemcpyHostToDevice, p->stream));
     CK(pm_launch_prior(make_frame(p), p->S.planes, p->d_vxy, p->d_tris, n_tris, p->d_tri_planes, p->d_mask, p->d_prior, p->d_prior_count,
                        p->stream));
+    p->has_prior = true;
+    // the count is only fetched (and the stream only drained) when the caller asks for it: without this the host would
+    // sit here while it could already be enqueuing the next run or triangulating the next image
+    if (n_prior_pixels) return mpmvs_get_prior_pixels(p, n_prior_pixels);
+    return MPMVS_OK;
+}
+
+int mpmvs_get_prior_pixels(mpmvs_problem* p, int* n_prior_pixels) {
+    if (!p || !n_prior_pixels || !p->has_prior || !p->d_prior_count) return MPMVS_E_ARG;
+    CK(cudaSetDevice(p->device));
     unsigned int count = 0;
     CK(cudaMemcpyAsync(&count, p->d_prior_count, sizeof(count), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
-    if (n_prior_pixels) *n_prior_pixels = (int)count;
-    p->has_prior = true;
+    *n_prior_pixels = (int)count;
     return MPMVS_OK;
 }
 
@@ -891,12 +909,12 @@ int mpmvs_build_prior(mpmvs_problem* p, mpmvs_prior_stats* stats) {
         d.triangles(tris);
     }
     const auto t2 = clk::now();
-    int npx = 0;
-    rc = mpmvs_prior_from_triangles(p, xy.data(), nv, tris.data(), (int)(tris.size() / 3), &npx);
+    // vertices and triangles are copied with cudaMemcpyAsync from pageable vectors: the runtime stages them before returning
+    rc = mpmvs_prior_from_triangles(p, xy.data(), nv, tris.data(), (int)(tris.size() / 3), nullptr);
     if (rc) return rc;
     const auto t3 = clk::now();
     if (stats) {
-        stats->n_vertices = nv; stats->n_triangles = (int)(tris.size() / 3); stats->n_prior_pixels = npx;
+        stats->n_vertices = nv; stats->n_triangles = (int)(tris.size() / 3); stats->n_prior_pixels = -1;  /* mpmvs_get_prior_pixels */
         stats->pick_ms = ms(t0, t1); stats->delaunay_ms = ms(t1, t2); stats->raster_ms = ms(t2, t3); stats->total_ms = ms(t0, t3);
     }
     return MPMVS_OK;

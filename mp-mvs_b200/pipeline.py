@@ -47,6 +47,9 @@ def stage_seed(seed: int, ref_id: int, stage: int) -> int:
 @dataclass
 class PipelineConfig:
     geom_iterations: int = 2          # "Geometric consistency iterations"
+    planar_prior: bool = False        # "Planer prior"
+    geom_planar_prior: bool = False   # "Geometric consistency planer prior"
+    in_flight: int = 2                # reference images a rank keeps in flight (host threads; the C ABI releases the GIL)
     max_src: int = 20                 # "Max source images num"
     seed: int = 0
     tex_format: int = 2               # capi.TEX_U8: views are 8-bit grey levels as decoded from the JPEGs
@@ -56,7 +59,7 @@ class PipelineConfig:
 @dataclass
 class PassStats:
     name: str
-    device_ms: float = 0.0           # sum of the Run() device times of this rank
+    device_ms: float = 0.0           # wall/device time of the pass on this rank (all its reference images)
     exchange_ms: float = 0.0
     n_refs: int = 0
 
@@ -69,16 +72,22 @@ class CudaEngine:
 
         self.pm = capi.PatchMatch(device)
         self.pm.set_problem_cached(cache, list(ids), cams_packed)
+        self.prior_stats = None
 
-    def run_photometric(self, seed: int):
-        self.pm.reset_params()
-        self.pm.set_geom_consistency_params(False, False)
-        self.pm.run_async(seed)
-
-    def run_geometric(self, seed: int, src_depth_ptrs: Sequence[int]):
-        self.pm.set_geom_consistency_params(True, False)
-        self.pm.set_src_depths_device(list(src_depth_ptrs))
-        self.pm.run_async(seed)
+    def process(self, seed: int, geom: bool, planar: bool, src_depth_ptrs: Optional[Sequence[int]] = None):
+        """The compute of one ProcessProblem(geom, planar) call (PatchMatch.cpp:516-609) on the resident state:
+        Run(); if planar: planar-prior stage + planar-prior Run(). Returns with the last run still in flight."""
+        pm = self.pm
+        pm.reset_params()                                   # a fresh PatchMatchCUDA object per call (PatchMatch.cpp:516)
+        pm.set_geom_consistency_params(geom, planar)
+        if geom:
+            pm.set_src_depths_device(list(src_depth_ptrs))
+        pm.run_async(seed)
+        if planar:
+            pm.set_planar_prior_params()
+            pm.set_geom_consistency_params(False, True)
+            self.prior_stats = pm.build_prior()             # blocks this host thread only
+            pm.run_async(seed ^ 0x5DEECE66D)
 
     def export_depth(self, dst_tensor):
         self.pm.export_depth_device(dst_tensor.data_ptr(), dst_tensor.stride(0) * 4)
@@ -203,29 +212,44 @@ class DensePipeline:
         return (time.time() - t0) * 1e3
 
     # ------------------------------------------------------------------------------------------ passes
-    def run(self):
-        if not self.engines:
-            self.setup()
-        st = PassStats("photometric", n_refs=len(self.my_refs))
-        for ref in self.my_refs:
-            self.engines[ref].run_photometric(stage_seed(self.cfg.seed, ref, 0))
+    def _run_pass(self, st: PassStats, stage: int, geom: bool, planar: bool, prev=None):
+        """One ProcessProblem per reference image of this rank, `in_flight` of them at a time on host threads."""
+        from concurrent.futures import ThreadPoolExecutor
+
+        def one(ref):
+            seed = stage_seed(self.cfg.seed, ref, stage)
+            if geom:
+                views = [prev[self.slot[i]] for i in self.problem_ids(ref)[1:]]
+                self.engines[ref].process(seed, True, planar, [v.data_ptr() for v in views] if self.tdev.type == "cuda" else views)
+            else:
+                self.engines[ref].process(seed, False, planar)
+
+        t0 = self._tick()
+        if self.cfg.in_flight > 1 and len(self.my_refs) > 1:
+            with ThreadPoolExecutor(self.cfg.in_flight) as ex:
+                list(ex.map(one, self.my_refs))
+        else:
+            for ref in self.my_refs:
+                one(ref)
         for ref in self.my_refs:
             self.engines[ref].synchronize()
-            st.device_ms += self.engines[ref].device_ms()
-        if self.cfg.geom_iterations > 0:
+        st.device_ms = self._tock(t0)
+
+    def run(self):
+        """The stage schedule of main() (main.cpp:20-41) over this rank's reference images."""
+        if not self.engines:
+            self.setup()
+        cfg = self.cfg
+        st = PassStats("photometric" + (" + planar prior" if cfg.planar_prior and not cfg.geom_planar_prior else ""), n_refs=len(self.my_refs))
+        self._run_pass(st, 0, False, cfg.planar_prior and not cfg.geom_planar_prior)
+        if cfg.geom_iterations > 0:
             self._exchange(st)
         self.stats.append(st)
-        for g in range(self.cfg.geom_iterations):
-            st = PassStats(f"geometric {g}", n_refs=len(self.my_refs))
-            prev = self.gathered
-            for ref in self.my_refs:
-                srcs = self.problem_ids(ref)[1:]
-                views = [prev[self.slot[i]] for i in srcs]
-                self.engines[ref].run_geometric(stage_seed(self.cfg.seed, ref, 1 + g), [v.data_ptr() for v in views] if self.tdev.type == "cuda" else views)
-            for ref in self.my_refs:
-                self.engines[ref].synchronize()
-                st.device_ms += self.engines[ref].device_ms()
-            if g + 1 < self.cfg.geom_iterations:
+        for g in range(cfg.geom_iterations):
+            planar = cfg.geom_planar_prior and g != cfg.geom_iterations - 1
+            st = PassStats(f"geometric {g}" + (" + planar prior" if planar else ""), n_refs=len(self.my_refs))
+            self._run_pass(st, 1 + g, True, planar, self.gathered)
+            if g + 1 < cfg.geom_iterations:
                 self._exchange(st)
             self.stats.append(st)
         return self.stats

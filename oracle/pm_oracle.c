@@ -854,3 +854,102 @@ void pmo_destroy(void *h) {
     free(P->planes); free(P->costs); free(P->rng); free(P->views); free(P->geom); free(P->prior); free(P->mask);
     free(P);
 }
+
+/* ------------------------------------------------------------------ host planar-prior stage (single-threaded, like the reference)
+ * Restatement of the host code ProcessProblem runs between the two Run()s (/root/reference/src/PatchMatch.cpp:532-609):
+ * GetTriangulateVertices (:782-853), the rasterisation loop (:554-579), GetPriorPlaneParams (:723-755), the depth-range
+ * check (:583-595) and the per-pixel expansion of CudaPlanarPriorInitialization (:984-993). The triangulation itself is
+ * NOT here: callers use cv2.Subdiv2D, the reference's own triangulator (:766-771). Used by the tests (small cases, against
+ * oracle/prior_oracle.py) and by bench.py's reference arm as the host stage of the reference pipeline, timed at -O2 on one
+ * core. cv::SVD::solveZ of the 3x4 system [X 1] is restated as the plane through the three points (its null vector). */
+int pmo_pick_vertices(const float *costs, const float *geom, int w, int h, int geom_variant, int *xy_out) {
+    int n = 0;
+    for (int row = 0; row < h; row += 5)
+        for (int col = 0; col < w; col += 5) {
+            const int c_bound = w < col + 5 ? w : col + 5, r_bound = h < row + 5 ? h : row + 5;
+            if (!geom_variant) {
+                float min_cost = 2.0f; int bx = 0, by = 0;
+                for (int r = row; r < r_bound; ++r)
+                    for (int c = col; c < c_bound; ++c) {
+                        const float cost = costs[r * w + c];
+                        if (cost < 2.0f && min_cost > cost) { bx = c; by = r; min_cost = cost; }
+                    }
+                if (min_cost < 0.1f) { xy_out[2 * n] = bx; xy_out[2 * n + 1] = by; ++n; }
+            } else {
+                float mc[3] = { 2.0f, 2.0f, 2.0f }; int px[3] = { 0, 0, 0 }, py[3] = { 0, 0, 0 };
+                float cost_sum = 0.0f;
+                for (int r = row; r < r_bound; ++r)
+                    for (int c = col; c < c_bound; ++c) {
+                        const float cost = costs[r * w + c];
+                        cost_sum += cost;
+                        if (cost < 1.0f && geom[r * w + c] < 0.4f && cost < mc[2]) {
+                            mc[2] = cost; px[2] = c; py[2] = r;
+                            for (int i = 1; i >= 0; --i) {
+                                if (mc[i] <= mc[i + 1]) break;
+                                float t = mc[i + 1]; mc[i + 1] = mc[i]; mc[i] = t;
+                                int tx = px[i + 1]; px[i + 1] = px[i]; px[i] = tx;
+                                int ty = py[i + 1]; py[i + 1] = py[i]; py[i] = ty;
+                            }
+                        }
+                    }
+                cost_sum = cost_sum / (r_bound * c_bound) * 0.85; /* :841, absolute coordinates in the divisor */
+                const float thresh = cost_sum > 0.2f ? cost_sum : 0.2f;
+                for (int i = 0; i < 3; ++i) {
+                    if (mc[i] < thresh) { xy_out[2 * n] = px[i]; xy_out[2 * n + 1] = py[i]; ++n; } else break;
+                }
+            }
+        }
+    return n;
+}
+
+/* tris: n_tris x 3 x (x, y) pixel coordinates. planes4: (h, w, 4) result of the previous Run (w = depth).
+ * Writes prior4 (h, w, 4) and mask (h, w); returns the number of prior pixels. */
+int pmo_prior_from_triangles(const int *tris, int n_tris, const float *planes4, const float *K, int w, int h, float depth_min,
+                             float depth_max, float *prior4, uint32_t *mask) {
+    float *fmask = (float *)calloc((size_t)w * h, sizeof(float));
+    f4 *tp = (f4 *)malloc(sizeof(f4) * (size_t)(n_tris > 0 ? n_tris : 1));
+    const float fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+    for (int t = 0; t < n_tris; ++t) {
+        const int *T = tris + 6 * t;
+        const int x1 = T[0], y1 = T[1], x2 = T[2], y2 = T[3], x3 = T[4], y3 = T[5];
+        float L01 = sqrt(pow(x1 - x2, 2) + pow(y1 - y2, 2)), L02 = sqrt(pow(x1 - x3, 2) + pow(y1 - y3, 2));
+        float L12 = sqrt(pow(x2 - x3, 2) + pow(y2 - y3, 2));
+        float max_edge = L01 > (L02 > L12 ? L02 : L12) ? L01 : (L02 > L12 ? L02 : L12);
+        float step = 1.0 / max_edge;
+        for (float p = 0; p < 1.0; p += step)
+            for (float q = 0; q < 1.0 - p; q += step) {
+                int x = p * x1 + q * x2 + (1.0 - p - q) * x3;
+                int y = p * y1 + q * y2 + (1.0 - p - q) * y3;
+                if (x >= 0 && x < w && y >= 0 && y < h) fmask[y * w + x] = t + 1.0;
+            }
+        double X[3][3];
+        for (int k = 0; k < 3; ++k) { /* Get3DPointonRefCam, :200-209 */
+            const int x = T[2 * k], y = T[2 * k + 1];
+            const float depth = planes4[((size_t)y * w + x) * 4 + 3];
+            X[k][0] = depth * (x - cx) / fx; X[k][1] = depth * (y - cy) / fy; X[k][2] = depth;
+        }
+        const double ux = X[1][0] - X[0][0], uy = X[1][1] - X[0][1], uz = X[1][2] - X[0][2];
+        const double vx = X[2][0] - X[0][0], vy = X[2][1] - X[0][1], vz = X[2][2] - X[0][2];
+        double nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
+        double nn = sqrt(nx * nx + ny * ny + nz * nz), d = -(nx * X[0][0] + ny * X[0][1] + nz * X[0][2]);
+        if (d < 0) nn = -nn; /* :746-749 */
+        tp[t].x = (float)(nx / nn); tp[t].y = (float)(ny / nn); tp[t].z = (float)(nz / nn); tp[t].w = (float)(d / nn);
+    }
+    int count = 0;
+    for (int j = 0; j < h; ++j)
+        for (int i = 0; i < w; ++i) {
+            const size_t idx = (size_t)j * w + i;
+            mask[idx] = 0;
+            if (fmask[idx] > 0) {
+                const f4 n4 = tp[(int)fmask[idx] - 1];
+                float d = -n4.w * fx / ((i - cx) * n4.x + (fx / fy) * (j - cy) * n4.y + fx * n4.z); /* :650-653 */
+                if (d <= depth_max && d >= depth_min) {
+                    mask[idx] = (uint32_t)fmask[idx];
+                    memcpy(prior4 + 4 * idx, &n4, sizeof(f4));
+                    ++count;
+                }
+            }
+        }
+    free(fmask); free(tp);
+    return count;
+}

@@ -128,3 +128,38 @@ def build_prior(planes_world, costs, K, depth_min, depth_max, geom_costs=None, t
                     out_mask[j, i] = m
                     prior[j, i] = n4
     return prior, out_mask, verts, tris
+
+
+# ----------------------------------------------------------------------------- fast path (C loops in libpm_oracle.so)
+def build_prior_fast(planes_world, costs, K, depth_min, depth_max, geom_costs=None):
+    """Same stage with the loops in C (oracle/pm_oracle.c: pmo_pick_vertices, pmo_prior_from_triangles) and OpenCV's
+    Subdiv2D for the triangulation: what bench.py's reference arm runs as the reference pipeline's host stage."""
+    import ctypes as C
+    import os
+
+    import cv2
+
+    lib = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpm_oracle.so"))
+    h, w = costs.shape
+    costs = np.ascontiguousarray(costs, np.float32)
+    planes_world = np.ascontiguousarray(planes_world, np.float32)
+    g = None if geom_costs is None else np.ascontiguousarray(geom_costs, np.float32)
+    xy = np.empty((3 * ((w + 4) // 5) * ((h + 4) // 5), 2), np.int32)
+    n = lib.pmo_pick_vertices(costs.ctypes.data_as(C.c_void_p), None if g is None else g.ctypes.data_as(C.c_void_p), w, h,
+                              0 if g is None else 1, xy.ctypes.data_as(C.c_void_p))
+    verts = xy[:n]
+    sd = cv2.Subdiv2D((0, 0, w, h))
+    if n:
+        sd.insert(np.ascontiguousarray(verts, dtype=np.float32))
+    tl = sd.getTriangleList() if n >= 3 else np.zeros((0, 6), np.float32)
+    t = tl.astype(np.int32).reshape(-1, 3, 2)
+    ok = np.all((t[..., 0] >= 0) & (t[..., 0] < w) & (t[..., 1] >= 0) & (t[..., 1] < h), axis=1)
+    tris = np.ascontiguousarray(t[ok])
+    prior = np.zeros((h, w, 4), np.float32)
+    mask = np.zeros((h, w), np.uint32)
+    Kf = np.ascontiguousarray(np.asarray(K, np.float32).reshape(9))
+    lib.pmo_prior_from_triangles.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float,
+                                             C.c_void_p, C.c_void_p]
+    cnt = lib.pmo_prior_from_triangles(tris.ctypes.data, len(tris), planes_world.ctypes.data, Kf.ctypes.data, w, h,
+                                       C.c_float(depth_min), C.c_float(depth_max), prior.ctypes.data, mask.ctypes.data)
+    return prior, mask, verts, tris, cnt

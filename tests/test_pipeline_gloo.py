@@ -26,13 +26,11 @@ class OracleEngine:
         self.o = oracle_py.Oracle("cpu").set_problem([np.asarray(i, np.float32) for i in images], cams_packed)
         self.ms = 0.0
 
-    def run_photometric(self, seed):
-        self.o.set_geom_consistency_params(False, False)
-        self.o.run(seed)
-
-    def run_geometric(self, seed, src_depths):
-        self.o.set_geom_consistency_params(True, False)
-        self.o.set_src_depths([d.numpy() for d in src_depths])
+    def process(self, seed, geom, planar, src_depths=None):
+        assert not planar, "the CPU stand-in has no planar-prior stage"
+        self.o.set_geom_consistency_params(geom, False)
+        if geom:
+            self.o.set_src_depths([d.numpy() for d in src_depths])
         self.o.run(seed)
 
     def export_depth(self, dst):

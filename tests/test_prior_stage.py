@@ -159,3 +159,25 @@ def test_gpu_prior_stage_vs_restatement(geom_variant):
     acc0 = PKG.synth.accuracy_at(planes[..., 3], sc.gt_depth[2])
     print("accuracy before/after the prior run", acc0, acc)
     pm.destroy()
+
+
+def test_c_restatement_matches_python_restatement():
+    """oracle/pm_oracle.c's host prior stage (used at full size by bench.py's reference arm) against the line-by-line
+    numpy restatement, on a rendered scene with a synthetic converged state."""
+    import prior_oracle
+
+    sc = PKG.synth.make_eth3d_scene(width=120, height=81, n_views=3, n_src=2, jpeg=False)
+    rng = np.random.default_rng(5)
+    gt = sc.gt_depth[1]
+    planes = np.concatenate([sc.gt_normal[1], (np.where(gt > 0, gt, 3.0) * rng.uniform(0.99, 1.01, gt.shape))[..., None]], -1).astype(np.float32)
+    costs = rng.uniform(0.0, 0.3, gt.shape).astype(np.float32)
+    geom = rng.uniform(0.0, 0.8, gt.shape).astype(np.float32)
+    K = sc.cams[1].K
+    for g in (None, geom):
+        pw, mw, vw, tw = prior_oracle.build_prior(planes, costs, K, 1.0, 6.0, g)
+        pf, mf, vf, tf, cnt = prior_oracle.build_prior_fast(planes, costs, K, 1.0, 6.0, g)
+        np.testing.assert_array_equal(vw, vf)
+        np.testing.assert_array_equal(tw, tf)
+        assert (mw == mf).mean() > 0.9995 and cnt == int((mf > 0).sum())
+        both = (mw > 0) & (mw == mf)
+        assert np.abs(pw[both] - pf[both]).max() < 2e-3

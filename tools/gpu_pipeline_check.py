@@ -34,7 +34,9 @@ sc = synth.make_dtu_scene(width=W, height=H, grid=3, n_src=4, seed=2, jpeg=False
 entries = [io_formats.SceneEntry(ref_id=i, src_ids=[i] + [j for j, _ in sc.pairs[i]], estimate=True) for i in range(sc.num_views)]
 cams = {i: c for i, c in enumerate(sc.cams)}
 images = {i: im for i, im in enumerate(sc.images)}
-cfg = pipeline.PipelineConfig(geom_iterations=2, max_src=4, seed=5)
+cfg = pipeline.PipelineConfig(geom_iterations=2, max_src=4, seed=5, planar_prior=os.environ.get('PIPE_PLANAR', '0') == '1',
+                              geom_planar_prior=os.environ.get('PIPE_GEOMPLANAR', '0') == '1')
+tag = f"p{int(cfg.planar_prior)}g{int(cfg.geom_planar_prior)}"
 p = pipeline.DensePipeline(entries, cams, images, cfg, rank=rank, world=world, device=local, dist=dist)
 t = time.time()
 stats = p.run()
@@ -48,7 +50,7 @@ for ref, (planes, costs) in res.items():
                      "mean_cost": float(costs.mean())}
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump({"world": world, "rank": rank, "wall_s": dt, "stats": [s.__dict__ for s in stats], "refs": out},
-          open(os.path.join(ROOT, "gpurun_out", f"pipeline_w{world}_r{rank}.json"), "w"), indent=1)
+          open(os.path.join(ROOT, "gpurun_out", f"pipeline_{tag}_w{world}_r{rank}.json"), "w"), indent=1)
 print(f"rank {rank}/{world}: {len(res)} refs in {dt:.2f} s;", [(s.name, round(s.device_ms, 1), round(s.exchange_ms, 2)) for s in stats], flush=True)
 p.destroy()
 if dist is not None:
