@@ -1,0 +1,84 @@
+"""The C++ host mirror (mp-mvs_b200/csrc/PatchMatchCUDA.h, mpmvs_host.cpp, mpmvs_main.cpp): the reference's entry point
+(/root/reference/src/main.cpp) over the dense-folder layout, driven through the C ABI."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import PKG, ROOT, has_gpu
+
+MAIN = os.path.join(ROOT, "mp-mvs_b200", "mpmvs_main")
+
+
+def build_main():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "mp-mvs_b200", "csrc")])
+    assert os.path.exists(MAIN)
+
+
+def write_scene(tmp_path, width=320, height=240, **cfg):
+    sc = PKG.synth.make_dtu_scene(width=width, height=height, grid=3, n_src=4, seed=2, jpeg=True)
+    root = str(tmp_path / "dense")
+    PKG.synth.write_dense_folder(sc, root)
+    yaml = str(tmp_path / "config.yaml")
+    base = {"Input-folder": root, "Output-folder": root, "Max source images num": 4}
+    base.update(cfg)
+    PKG.io_formats.write_config(yaml, **base)
+    return sc, root, yaml
+
+
+@pytest.mark.skipif(has_gpu(), reason="only meaningful on a box without a GPU")
+def test_main_fails_loudly_without_gpu(tmp_path):
+    build_main()
+    sc, root, yaml = write_scene(tmp_path, 64, 48)
+    r = subprocess.run([MAIN, yaml], capture_output=True, text=True)
+    assert r.returncode != 0
+    assert "no CUDA device" in r.stdout          # no CPU fallback: the first mpmvs_create fails
+    assert "There are 9 depthmaps" in r.stdout   # config.yaml, pair.txt were parsed before that
+
+
+def test_main_reports_missing_inputs(tmp_path):
+    build_main()
+    r = subprocess.run([MAIN, str(tmp_path / "nope.yaml")], capture_output=True, text=True)
+    assert r.returncode != 0 and "can not open config file" in r.stdout
+    yaml = str(tmp_path / "c.yaml")
+    PKG.io_formats.write_config(yaml, **{"Input-folder": str(tmp_path), "Output-folder": str(tmp_path)})
+    r = subprocess.run([MAIN, yaml], capture_output=True, text=True)
+    assert r.returncode != 0 and "pair.txt" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["default_schedule", "photometric_only_resized"])
+def test_main_end_to_end(tmp_path, mode):
+    build_main()
+    if mode == "default_schedule":       # the shipped config: planar prior inside the first geom iteration, 2 geom iterations
+        sc, root, yaml = write_scene(tmp_path, **{"Geometric consistency iterations": 2, "Planer prior": 1,
+                                                  "Geometric consistency planer prior": 1})
+        scale = 1
+    else:                                # Max image size below the image size: PatchMatchInit's resize + K scaling path
+        sc, root, yaml = write_scene(tmp_path, **{"Geometric consistency iterations": 0, "Planer prior": 0,
+                                                  "Geometric consistency planer prior": 0, "Max image size": 160})
+        scale = 2
+    r = subprocess.run([MAIN, yaml, "--seed", "5", "--tex", "u8"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "cost time is" in r.stdout
+    out = os.path.join(root, "MPMVS")
+    assert os.path.getsize(os.path.join(out, "MPMVS_model.ply")) > 1000
+    accs = []
+    for i in range(sc.num_views):
+        d = PKG.io_formats.read_dmb(os.path.join(out, f"2333_{i:08d}", "depths.dmb"))
+        n = PKG.io_formats.read_dmb(os.path.join(out, f"2333_{i:08d}", "normals.dmb"))
+        c = PKG.io_formats.read_dmb(os.path.join(out, f"2333_{i:08d}", "costs.dmb"))
+        gt = sc.gt_depth[i][::scale, ::scale] if scale > 1 else sc.gt_depth[i]
+        assert d.shape == (240 // scale, 320 // scale) and n.shape == d.shape + (3,) and c.shape == d.shape
+        assert np.isfinite(d).all() and abs(float(np.linalg.norm(n, axis=-1).mean()) - 1) < 1e-3
+        if scale == 1:
+            accs.append(PKG.synth.accuracy_at(d, gt)[2])
+        else:   # pixel (x, y) of the half-size image sees the scene along the ray of full-size pixel ~(2x+0.5, 2y+0.5)
+            accs.append(float(100 * (np.abs(d - gt) < 0.05 * gt)[gt > 0].mean()))
+    print(mode, "accuracy per view", [round(a, 1) for a in accs])
+    assert np.median(accs) > (95 if scale == 1 else 85)
+    with open(os.path.join(out, "MPMVS_model.ply"), "rb") as f:
+        head = f.read(400).decode("latin1")
+    nv = int(head.split("element vertex ")[1].split("\n")[0])
+    assert nv > 1000
