@@ -144,6 +144,15 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(workload: str):
+    """DRAM bytes per pm_sweep_kernel launch from the committed ncu capture of this workload (profiles/), else None."""
+    try:
+        j = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        return j["dram_bytes_per_launch"] if j.get("workload") == workload else None
+    except Exception:
+        return None
+
+
 def measured_peaks() -> dict:
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -339,10 +348,12 @@ def run_ours(args, rank, world, local_rank, prob, barrier, allmax):
                                "n_sweep_launches": n_sweeps, "host_delaunay": round(dl_ms / args.steps, 3),
                                "note": "kernels timed alone in a sequential pass; value/e2e keep `in_flight` images in flight"},
         "roofline": {"bound": "l1tex", "kernel": "pm_sweep_kernel", "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": "GB/s",
-                     "frac": round(achieved / peak, 4), "traffic": None,
+                     "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args.workload),
                      "peak_source": "4 bilinear/clk/SM x 148 SM x measured sm_max_mhz x 16 B (profiles/r01_tex_microbench.log reaches 3.98/clk/SM)",
                      "executed_taps_per_step": int(taps_sweeps), "reference_equivalent_taps_per_step": int(ref_equiv_taps),
                      "gtaps_per_s": round(taps_sweeps / sweep_s / 1e9, 2),
+                     "achieved_per_launch_bytes": int(taps_sweeps * BYTES_PER_TAP / max(1, n_sweeps)),
+                     "traffic_note": "DRAM bytes per sweep launch (ncu, profiles/r01_ncu_traffic.json); ~ the per-pixel state a half-sweep must read and write (780 MB), the kernel is L1/TEX-bound, not DRAM-bound",
                      "hbm_peak_gbs": peaks.get("hbm_gbs")},
         "clocks": clocks,
         "checksum_mean_cost": round(checksum, 6), "accuracy_2_5_10cm": [round(a, 3) for a in acc],

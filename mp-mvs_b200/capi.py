@@ -93,6 +93,7 @@ def lib() -> C.CDLL:
         "mpmvs_set_device_state": [vp, vp, vp, vp, vp, vp],
         "mpmvs_ncc_map": [vp, vp, i, vp],
         "mpmvs_geom_map": [vp, vp, vp],
+        "mpmvs_ncc_bench": [vp, vp, i, i, i, i, fp, C.POINTER(u64)],
         "mpmvs_uniform_stream": [u64, i, i, i, vp],
         "mpmvs_delaunay": [vp, i, i, i, vp, i, C.POINTER(i)],
         "mpmvs_build_prior": [vp, vp],
@@ -381,6 +382,13 @@ class PatchMatch:
         out = np.empty((self.n - 1, self.hgt, self.w), np.float32)
         _ck(lib().mpmvs_ncc_map(self.h, p.ctypes.data, int(scale), out.ctypes.data), "ncc_map")
         return out
+
+    def ncc_bench(self, planes4, scale: int, taps: int, n_views: int, reps: int):
+        """(ms of one pass, executed NCC evaluations) of the NCC microbenchmark kernel."""
+        p = np.ascontiguousarray(planes4, dtype=np.float32)
+        ms, cnt = C.c_float(), C.c_uint64()
+        _ck(lib().mpmvs_ncc_bench(self.h, p.ctypes.data, scale, taps, n_views, reps, C.byref(ms), C.byref(cnt)), "ncc_bench")
+        return float(ms.value), int(cnt.value)
 
     def geom_map(self, planes4):
         p = np.ascontiguousarray(planes4, dtype=np.float32)

@@ -789,6 +789,34 @@ int mpmvs_ncc_map(mpmvs_problem* p, const float* planes4_host, int scale, float*
     return (int)e;
 }
 
+int mpmvs_ncc_bench(mpmvs_problem* p, const float* planes4_host, int scale, int taps_per_side, int n_views, int reps, float* ms,
+                    uint64_t* ncc_evaluations) {
+    if (!p || !planes4_host || p->n < 2 || n_views < 1 || n_views > p->n - 1 || reps < 1 || !ms) return MPMVS_E_ARG;
+    CK(cudaSetDevice(p->device));
+    pm_f4* dp = nullptr;
+    float* dout = nullptr;
+    unsigned long long* dc = nullptr;
+    CK(cudaMalloc((void**)&dp, p->wh * sizeof(pm_f4)));
+    cudaError_t e = cudaMalloc((void**)&dout, p->wh * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dc, sizeof(unsigned long long));
+    if (e != cudaSuccess) { cudaFree(dp); cudaFree(dout); return (int)e; }
+    cudaMemcpyAsync(dp, planes4_host, p->wh * sizeof(pm_f4), cudaMemcpyHostToDevice, p->stream);
+    cudaMemsetAsync(dc, 0, sizeof(unsigned long long), p->stream);
+    const PmFrame F = make_frame(p);
+    // one counting pass (also warm-up), then the timed pass without the counter
+    e = pm_launch_ncc_bench(F, p->dviews, dp, scale, taps_per_side, n_views, reps, dout, dc, p->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(p->ev0, p->stream);
+    if (e == cudaSuccess) e = pm_launch_ncc_bench(F, p->dviews, dp, scale, taps_per_side, n_views, reps, dout, nullptr, p->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(p->ev1, p->stream);
+    if (e == cudaSuccess) e = cudaEventSynchronize(p->ev1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(ms, p->ev0, p->ev1);
+    unsigned long long cnt = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&cnt, dc, sizeof(cnt), cudaMemcpyDeviceToHost);
+    if (ncc_evaluations) *ncc_evaluations = cnt;
+    cudaFree(dp); cudaFree(dout); cudaFree(dc);
+    return (int)e;
+}
+
 int mpmvs_geom_map(mpmvs_problem* p, const float* planes4_host, float* out_host) {
     if (!p || !planes4_host || !out_host || p->n < 2) return MPMVS_E_ARG;
     if (!p->has_depths) return MPMVS_E_STATE;

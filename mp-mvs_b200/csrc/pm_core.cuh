@@ -39,6 +39,9 @@
 #ifndef PM_VIEW_OUTER
 #define PM_VIEW_OUTER 0  // 1: the 8 propagation candidates are scored view by view (a source view's window stays in L1/TEX)
 #endif
+#ifndef PM_DEBUG_MAXH
+#define PM_DEBUG_MAXH 14   // measurement only: < 14 truncates the hypothesis loop (results are then wrong)
+#endif
 #ifndef PM_EARLY_OUT
 #define PM_EARLY_OUT 1   // stop scoring a refinement proposal once it can no longer be accepted (result-identical)
 #endif
@@ -218,6 +221,18 @@ PM_HD constexpr float pm_tap_dist(int u, int v) {
                                    : 7.07106781187f;
 }
 
+// General window (NCC microbenchmark, BASELINE.json config 5): TAPS x TAPS taps at offsets (2a - (TAPS-1)) * step/2, i.e. a
+// (2*(TAPS-1)+1)-pixel window at step 2. The reference only has TAPS = 6 (cu:342-346,365,373), which keeps its exact constants.
+PM_HD constexpr float pm_csqrt(float x) {
+    float r = x > 1.f ? x : 1.f;
+    for (int i = 0; i < 40; ++i) r = 0.5f * (r + x / r);
+    return r;
+}
+template <int TAPS>
+PM_HD constexpr float pm_tap_dist_n(int u, int v) {
+    return TAPS == 6 ? pm_tap_dist(u, v) : pm_csqrt((float)(u * u + v * v));
+}
+
 // Reference-side statistics of one pixel at one scale: hypothesis-invariant (hoisted out of cu:341-414).
 struct PmRefStats {
     float r0;        // centre intensity
@@ -226,19 +241,19 @@ struct PmRefStats {
     float var_r;     // weighted variance of the reference patch
 };
 
-template <int SCALE, class Ctx>
+template <int SCALE, class Ctx, int TAPS = 6>
 PM_HD PmRefStats pm_ref_stats(const Ctx& c, const PmFrame& F) {
     constexpr int HS = 1 << SCALE;  // step/2: taps at (2a-5)*HS
     PmRefStats st;
     st.r0 = c.ref(0, 0);
     float sw = 0.f, swr = 0.f, swrr = 0.f;
 #pragma unroll
-    for (int a = 0; a < 6; ++a) {
+    for (int a = 0; a < TAPS; ++a) {
 #pragma unroll
-        for (int b = 0; b < 6; ++b) {
-            const int u = 2 * a - 5, v = 2 * b - 5;
+        for (int b = 0; b < TAPS; ++b) {
+            const int u = 2 * a - (TAPS - 1), v = 2 * b - (TAPS - 1);
             const float r = c.ref(u * HS, v * HS);
-            const float w = pm_ex2(fmaf(fabsf(r - st.r0), -F.col_k, (HS * pm_tap_dist(u, v)) * F.spat_k));
+            const float w = pm_ex2(fmaf(fabsf(r - st.r0), -F.col_k, (HS * pm_tap_dist_n<TAPS>(u, v)) * F.spat_k));
             sw += w;
             swr = fmaf(w, r, swr);
             swrr = fmaf(w * r, r, swrr);
@@ -263,7 +278,7 @@ PM_HD PmHyp pm_hyp(const PmFrame& F, const pm_f4& pl, int x, int y) {
 }
 
 // ComputeBilateralNCC, cu:325-414: cost of hypothesis `hyp` at pixel (x,y) against source view v.
-template <int SCALE, class Ctx>
+template <int SCALE, class Ctx, int TAPS = 6>
 PM_HD float pm_ncc(const Ctx& c, const PmFrame& F, const PmRefStats& st, int v, const PmHyp& hyp, int x, int y,
                    uint32_t& nexec) {
     constexpr int HS = 1 << SCALE;
@@ -282,19 +297,19 @@ PM_HD float pm_ncc(const Ctx& c, const PmFrame& F, const PmRefStats& st, int v, 
     const float Vx = fmaf(V.b[0], hyp.my, V.A[1]), Vy = fmaf(V.b[1], hyp.my, V.A[4]), Vz = fmaf(V.b[2], hyp.my, V.A[7]);
     float s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-    for (int a = 0; a < 6; ++a) {
-        const int i = (2 * a - 5) * HS;
+    for (int a = 0; a < TAPS; ++a) {
+        const int i = (2 * a - (TAPS - 1)) * HS;
         const float Xa = fmaf((float)i, Ux, X0), Ya = fmaf((float)i, Uy, Y0), Za = fmaf((float)i, Uz, Z0);
 #pragma unroll
-        for (int b = 0; b < 6; ++b) {
-            const int j = (2 * b - 5) * HS;
+        for (int b = 0; b < TAPS; ++b) {
+            const int j = (2 * b - (TAPS - 1)) * HS;
             const float Z = fmaf((float)j, Vz, Za);
             const float rz = 1.0f / Z;
             const float xs = fmaf(fmaf((float)j, Vx, Xa), rz, 0.5f);
             const float ys = fmaf(fmaf((float)j, Vy, Ya), rz, 0.5f);
             const float s = c.src(v, xs, ys);
             const float r = c.ref(i, j);
-            const float w = pm_ex2(fmaf(fabsf(r - st.r0), -F.col_k, (HS * pm_tap_dist(2 * a - 5, 2 * b - 5)) * F.spat_k));
+            const float w = pm_ex2(fmaf(fabsf(r - st.r0), -F.col_k, (HS * pm_tap_dist_n<TAPS>(2 * a - (TAPS - 1), 2 * b - (TAPS - 1))) * F.spat_k));
             const float ws = w * s;
             s1 += ws;
             s2 = fmaf(ws, s, s2);
@@ -464,7 +479,7 @@ PM_HD void pm_sweep_pixel(const Ctx& c, const PmFrame& F, const PmState& S, int 
     }
 #endif
 #pragma unroll 1
-    for (int h = PM_VIEW_OUTER ? 8 : 0; h < 14; ++h) {
+    for (int h = PM_VIEW_OUTER ? 8 : 0; h < PM_DEBUG_MAXH; ++h) {
         if (h == 8) {
             // ---- view selection (cu:821-878)
             uint32_t nb[4];  // neighbour masks: up / down / left / right, gated by the flags of regions 0..3 (cu:824-830)

@@ -170,6 +170,38 @@ __global__ void __launch_bounds__(BW* BH, MIN_BLOCKS) pm_ncc_map_kernel(const Pm
     for (int v = 0; v < F.nsrc; ++v) out[(size_t)v * F.W * F.H + idx] = pm_ncc<SCALE>(c, F, st, v, hyp, x, y, nexec);
 }
 
+// NCC microbenchmark (BASELINE.json config 5): TAPS x TAPS window, the first `nviews` source views, `reps` evaluations per
+// (pixel, view) with the plane nudged per repetition so the fetches are not loop-invariant; out[idx] = sum of the costs.
+template <int SCALE, int TAPS, bool SC>
+__global__ void __launch_bounds__(BW* BH, MIN_BLOCKS) pm_ncc_bench_kernel(const PmFrame F, const PmView* gviews, const pm_f4* planes,
+                                                               int nviews, int reps, float* out, unsigned long long* counter) {
+    using T = Tile<SCALE, BH>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PmView* sviews = reinterpret_cast<PmView*>(smem_raw);
+    float* tile = reinterpret_cast<float*>(smem_raw + PM_MAX_SRC * sizeof(PmView));
+    const int x0 = blockIdx.x * BW, y0 = blockIdx.y * BH;
+    stage_tile<SCALE, BH>(tile, sviews, gviews, F, x0, y0);
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= F.W || y >= F.H) return;
+    DevCtx<T::PITCH, false, SC> c;
+    c.centre = tile + (threadIdx.y + T::R) * T::PITCH + (threadIdx.x + T::R);
+    c.views = sviews;
+    c.tex = (cudaTextureObject_t)F.tex;
+    c.scale = F.tex_scale;
+    const int idx = y * F.W + x;
+    const PmRefStats st = pm_ref_stats<SCALE, decltype(c), TAPS>(c, F);
+    pm_f4 pl = planes[idx];
+    float acc = 0.f;
+    uint32_t nexec = 0;
+    for (int r = 0; r < reps; ++r) {
+        const PmHyp hyp = pm_hyp(F, pl, x, y);
+        for (int v = 0; v < nviews; ++v) acc += pm_ncc<SCALE, decltype(c), TAPS>(c, F, st, v, hyp, x, y, nexec);
+        pl.w *= 1.0005f;
+    }
+    out[idx] = acc;
+    if (counter) atomicAdd(counter, (unsigned long long)nexec);
+}
+
 __global__ void __launch_bounds__(BW* BH) pm_geom_map_kernel(const PmFrame F, const PmView* gviews, const pm_f4* planes,
                                                               float* out) {
     __shared__ PmView sviews[PM_MAX_SRC];
@@ -300,6 +332,22 @@ cudaError_t pm_launch_ncc_map(const PmFrame& F, const PmView* gviews, const pm_f
         pm_ncc_map_kernel<decltype(s)::value, decltype(cl)::value, decltype(sc)::value>
             <<<grid_full(F.W, F.H), dim3(BW, BH), smem_bytes<decltype(s)::value, BH>(), st>>>(F, gviews, planes, out);
     });
+}
+
+cudaError_t pm_launch_ncc_bench(const PmFrame& F, const PmView* gviews, const pm_f4* planes, int scale, int taps, int nviews, int reps,
+                                float* out, unsigned long long* counter, cudaStream_t st) {
+    if (F.soft_clamp || taps < 3 || taps > 6 || scale < 0 || scale > 2) return cudaErrorInvalidValue;
+    const bool sc = F.tex_scale != 1.0f;
+    const dim3 g = grid_full(F.W, F.H), b(BW, BH);
+#define PM_NB(S, T)                                                                                                    \
+    if (scale == S && taps == T) {                                                                                     \
+        if (sc) pm_ncc_bench_kernel<S, T, true><<<g, b, smem_bytes<S, BH>(), st>>>(F, gviews, planes, nviews, reps, out, counter);  \
+        else pm_ncc_bench_kernel<S, T, false><<<g, b, smem_bytes<S, BH>(), st>>>(F, gviews, planes, nviews, reps, out, counter);    \
+    }
+    PM_NB(0, 3) PM_NB(0, 4) PM_NB(0, 5) PM_NB(0, 6) PM_NB(1, 6) PM_NB(2, 6)
+#undef PM_NB
+    if (scale > 0 && taps != 6) return cudaErrorInvalidValue;
+    return cudaGetLastError();
 }
 
 cudaError_t pm_launch_geom_map(const PmFrame& F, const PmView* gviews, const pm_f4* planes, float* out, cudaStream_t st) {

@@ -11,6 +11,8 @@ cudaError_t pm_launch_sweep(const PmFrame& F, const PmState& S, const PmView* gv
 cudaError_t pm_launch_finalize(const PmFrame& F, const PmState& S, cudaStream_t st);
 cudaError_t pm_launch_ncc_map(const PmFrame& F, const PmView* gviews, const pm_f4* planes, int scale, float* out,
                               cudaStream_t st);
+cudaError_t pm_launch_ncc_bench(const PmFrame& F, const PmView* gviews, const pm_f4* planes, int scale, int taps, int nviews, int reps,
+                                float* out, unsigned long long* counter, cudaStream_t st);
 cudaError_t pm_launch_geom_map(const PmFrame& F, const PmView* gviews, const pm_f4* planes, float* out, cudaStream_t st);
 // out_fmt: 0 = float32, 1 = float16, 2 = uint8 (MPMVS_TEX_*); output rows are dense
 cudaError_t pm_launch_convert(const void* in, size_t in_pitch, int in_is_u8, void* out, int out_fmt, int W, int H, cudaStream_t st);
