@@ -350,3 +350,57 @@ def test_u8_view_storage_matches_float_storage(capi, oracle, pkg):
     ao, ar = synth.accuracy_at(po[0][..., 3], gt), synth.accuracy_at(pr[0][..., 3], gt)
     assert all(abs(x - y) <= 0.5 for x, y in zip(ao, ar))
     pm.destroy(); ref.destroy()
+
+
+def test_live_ragged_views_and_max_sources(capi, oracle, pkg):
+    """Edge cases of the view set: (a) source images smaller than the reference image (the layered array then needs
+    coordinate clamping per view), (b) the maximum of 32 sources (one bit each in the 32-bit view mask, PatchMatch.cu:25-33)."""
+    need_ref(oracle)
+    synth, io = pkg.synth, pkg.io_formats
+    # (a) crop two of the four sources (top-left crop keeps K valid)
+    sc = synth.make_dtu_scene(width=128, height=96, grid=3, n_src=4, seed=2, jpeg=False)
+    ids, imgs, cams = problem_arrays(sc, 4)
+    imgs = [i.copy() for i in imgs]
+    cams = cams.copy()
+    for k, (w, h) in ((1, (100, 96)), (3, (128, 70))):
+        imgs[k] = np.ascontiguousarray(imgs[k][:h, :w])
+        cams["width"][k], cams["height"][k] = w, h
+    rnd = random_planes(dict(scene=sc, ref=4))
+    pm = capi.PatchMatch(0).set_problem(imgs, cams)
+    ref = oracle.Oracle("ref").set_problem(imgs, cams)
+    for s in (0, 2):
+        check_cost_map("dtu5", pm.ncc_map(rnd, s), ref.ncc_map(rnd, s))
+    for o in (pm, ref):
+        o.set_geom_consistency_params(False, False)
+        o.init_only(SEED)
+    sr = ref.get_state()
+    check_state("dtu5", pm.get_state(), sr, "gpu", planes_exact=True)
+    pm.set_dev_state(sr)
+    pm.half_sweep(0, 0, 1); ref.half_sweep(0, 0, 1)
+    check_state("dtu5", pm.get_state(), ref.get_state(), "gpu", upd=colour_mask(96, 128, 0))
+    pm.destroy(); ref.destroy()
+    # (b) 32 sources
+    sc = synth.make_dtu_scene(width=64, height=48, grid=6, n_src=32, seed=2, jpeg=False)
+    ids, imgs, cams = problem_arrays(sc, 14, 32)
+    assert len(ids) == 33
+    pm = capi.PatchMatch(0).set_problem(imgs, cams)
+    ref = oracle.Oracle("ref").set_problem(imgs, cams)
+    for o in (pm, ref):
+        o.set_geom_consistency_params(False, False)
+        o.init_only(SEED)
+    sr = ref.get_state()
+    check_state("dtu5", pm.get_state(), sr, "gpu", planes_exact=True)
+    pm.set_dev_state(sr)
+    pm.half_sweep(1, 0, 0); ref.half_sweep(1, 0, 0)
+    a, b = pm.get_state(), ref.get_state()
+    check_state("dtu5", a, b, "gpu", upd=colour_mask(48, 64, 1))
+    assert (a["views"] >> 16).max() > 0            # views beyond the 16th do get selected
+    pm.run(3); ref.run(3)
+    gt = sc.gt_depth[14]
+    ao, ar = synth.accuracy_at(pm.result()[0][..., 3], gt), synth.accuracy_at(ref.result()[0][..., 3], gt)
+    assert all(abs(x - y) < 3.0 for x, y in zip(ao, ar)), (ao, ar)
+    pm.destroy(); ref.destroy()
+    with pytest.raises(capi.MpmvsError):            # 33 sources do not fit the mask
+        sc2 = synth.make_dtu_scene(width=32, height=24, grid=6, n_src=33, seed=2, jpeg=False)
+        ids2, imgs2, cams2 = problem_arrays(sc2, 14, 33)
+        capi.PatchMatch(0).set_problem(imgs2, cams2)
