@@ -27,6 +27,7 @@ class Delaunay {
         // The bounding triangle of cv::Subdiv2D::initDelaunay for the rect (0, 0, width, height): with these three outer
         // vertices the hull slivers that OpenCV's triangulation lacks are missing here too (same prior coverage at the borders).
         const int64_t m = 3 * (int64_t)(width > height ? width : height);
+        small_ = m <= 3 * 4096;
         px_[n] = m;      py_[n] = 0;
         px_[n + 1] = 0;  py_[n + 1] = m;
         px_[n + 2] = -m; py_[n + 2] = -m;
@@ -53,12 +54,27 @@ class Delaunay {
     std::vector<int64_t> px_, py_;
     std::vector<Tri> tris_;
     int last_;
+    bool small_ = false;
     std::vector<int> stack_;
 
     int64_t orient(int a, int b, int c) const {
         return (px_[b] - px_[a]) * (py_[c] - py_[a]) - (py_[b] - py_[a]) * (px_[c] - px_[a]);
     }
-    // > 0 iff d lies strictly inside the circumcircle of the positively oriented triangle (a, b, c)
+    // > 0 iff d lies strictly inside the circumcircle of the positively oriented triangle (a, b, c).
+    // |det| <= 12 D^4 for coordinate differences <= D: with the bounding triangle at 3 * max(w, h), 64-bit integers are
+    // exact up to 4096-pixel images (D = 24576); larger images take the 128-bit path.
+    int incircle_sign(int a, int b, int c, int d) const {
+        if (small_) {
+            const int64_t ax = px_[a] - px_[d], ay = py_[a] - py_[d];
+            const int64_t bx = px_[b] - px_[d], by = py_[b] - py_[d];
+            const int64_t cx = px_[c] - px_[d], cy = py_[c] - py_[d];
+            const int64_t a2 = ax * ax + ay * ay, b2 = bx * bx + by * by, c2 = cx * cx + cy * cy;
+            const int64_t det = ax * (by * c2 - b2 * cy) - ay * (bx * c2 - b2 * cx) + a2 * (bx * cy - by * cx);
+            return det > 0 ? 1 : (det < 0 ? -1 : 0);
+        }
+        const __int128 det = incircle(a, b, c, d);
+        return det > 0 ? 1 : (det < 0 ? -1 : 0);
+    }
     __int128 incircle(int a, int b, int c, int d) const {
         const __int128 ax = px_[a] - px_[d], ay = py_[a] - py_[d];
         const __int128 bx = px_[b] - px_[d], by = py_[b] - py_[d];
@@ -166,7 +182,7 @@ class Delaunay {
             const int ku = index_of_neighbour(U, t);
             const int q = U.v[ku];
             const int a = T.v[nxt(kp)], b = T.v[prv(kp)];   // shared edge (a, b); T = (p, a, b), U = (q, b, a)
-            if (incircle(p, a, b, q) <= 0) continue;
+            if (incircle_sign(p, a, b, q) <= 0) continue;
             // flip (a, b) -> (p, q):  T = (p, a, q), U = (p, q, b)
             const int n_pa = T.n[prv(kp)];   // across (p, a): opposite b
             const int n_bp = T.n[nxt(kp)];   // across (b, p): opposite a
