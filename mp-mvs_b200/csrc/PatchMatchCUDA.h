@@ -40,6 +40,7 @@ struct Triangle { Point pt1, pt2, pt3; };          // PatchMatch.h:69-72
 struct GrayImage {                                 // float grey levels 0..255, row-major (cv::Mat CV_32FC1 of PatchMatchInit)
     int width = 0, height = 0;
     std::vector<float> px;
+    std::vector<unsigned char> u8;                  // the same pixels as decoded, when the image was not resized (8-bit upload path)
     bool empty() const { return px.empty(); }
 };
 struct Scene {                                     // utility.h:17-26
@@ -76,8 +77,18 @@ GrayImage resizeLinear(const GrayImage& src, int new_cols, int new_rows);       
 // ------------------------------------------------------------------------------------------------ the class
 class PatchMatchCUDA {
   public:
-    explicit PatchMatchCUDA(int device = 0) { check(mpmvs_create(device, nullptr, &h_), "mpmvs_create"); }
-    ~PatchMatchCUDA() { if (h_) mpmvs_destroy(h_); }
+    // The reference constructs one object per ProcessProblem call and Release()s it (PatchMatch.cpp:516,637). Handles are
+    // pooled per device here, so that costs one mpmvs_reset_params instead of a round of cudaMalloc/cudaFree, texture
+    // creation and pinned allocations.
+    explicit PatchMatchCUDA(int device = 0) : device_(device) {
+        std::vector<mpmvs_problem*>& pool = handle_pool(device);
+        if (!pool.empty()) { h_ = pool.back(); pool.pop_back(); check(mpmvs_reset_params(h_), "mpmvs_reset_params"); }
+        else check(mpmvs_create(device, nullptr, &h_), "mpmvs_create");
+    }
+    ~PatchMatchCUDA() { if (h_) handle_pool(device_).push_back(h_); }
+    static void ReleasePool() {
+        for (auto& kv : pools()) { for (mpmvs_problem* h : kv.second) mpmvs_destroy(h); kv.second.clear(); }
+    }
     PatchMatchCUDA(const PatchMatchCUDA&) = delete;
     PatchMatchCUDA& operator=(const PatchMatchCUDA&) = delete;
 
@@ -88,7 +99,7 @@ class PatchMatchCUDA {
     }
     void SetPlanarPriorParams() { planar_ = true; check(mpmvs_set_planar_prior_params(h_), "SetPlanarPriorParams"); }
     void SetFolder(const std::string& in, const std::string& out) { input_folder_ = in; output_folder_ = out; }
-    void SetTexFormat(int fmt) { check(mpmvs_set_tex_format(h_, fmt), "SetTexFormat"); }
+    void SetTexFormat(int fmt) { tex_format_ = fmt; check(mpmvs_set_tex_format(h_, fmt), "SetTexFormat"); }
 
     // PatchMatch.cpp:863-958: load images + cameras of Scenes[ID].srcID, resize above max_image_size, depth range;
     // in geom mode load the sources' depths.dmb. Scenes is taken by reference: decoded images stay cached in it.
@@ -108,7 +119,7 @@ class PatchMatchCUDA {
     float GetMaxDepth() const { return depth_max_; }
     int GetReferenceImageWidth() const { return cameras_[0].width; }
     int GetReferenceImageHeight() const { return cameras_[0].height; }
-    const GrayImage& GetReferenceImage() const { return images_[0]; }
+    const GrayImage& GetReferenceImage() const { return *images_[0]; }
     float4 GetPlaneHypothesis(int index) const { return planes_[index]; }
     float GetCost(int index) const { return costs_[index]; }
     float GetGeomCost(int index) const { return geom_costs_[index]; }
@@ -120,8 +131,12 @@ class PatchMatchCUDA {
     void GetTriangulateVertices(std::vector<Point>& Vertices);                          // :782-853
 
   private:
+    static std::map<int, std::vector<mpmvs_problem*>>& pools() { static std::map<int, std::vector<mpmvs_problem*>> p; return p; }
+    static std::vector<mpmvs_problem*>& handle_pool(int device) { return pools()[device]; }
+    int device_ = 0;
+    int tex_format_ = MPMVS_TEX_F32;
     mpmvs_problem* h_ = nullptr;
-    std::vector<GrayImage> images_;
+    std::vector<const GrayImage*> images_;         // the decoded images cached in Scenes (not copied per call)
     std::vector<std::vector<float>> depths_;
     std::vector<Camera> cameras_;
     std::vector<float4> planes_;

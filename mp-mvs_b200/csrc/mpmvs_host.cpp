@@ -148,6 +148,7 @@ static bool readPgm(const std::string& path, GrayImage& out) {
     out.width = w; out.height = h;
     out.px.resize(buf.size());
     for (size_t i = 0; i < buf.size(); ++i) out.px[i] = (float)buf[i];      // convertTo(CV_32FC1), PatchMatch.cpp:882
+    out.u8 = std::move(buf);
     return true;
 }
 
@@ -178,6 +179,7 @@ static bool readJpegLuma(const std::string& path, GrayImage& out) {
     out.width = w; out.height = h;
     out.px.resize(buf.size());
     for (size_t i = 0; i < buf.size(); ++i) out.px[i] = (float)buf[i];
+    out.u8 = std::move(buf);
     return true;
 }
 #endif
@@ -193,7 +195,7 @@ bool readGrayImage(const std::string& image_folder, int id, GrayImage& out) {
 // cv::resize(src, dst, Size(new_cols, new_rows), 0, 0, INTER_LINEAR) for CV_32FC1 (PatchMatch.cpp:915): pixel-centre
 // mapping sx = (dx + 0.5) * scale - 0.5, source index clamped to the image, separable linear weights.
 GrayImage resizeLinear(const GrayImage& src, int new_cols, int new_rows) {
-    GrayImage dst;
+    GrayImage dst;                                  // (no 8-bit copy: resized pixels are not integers)
     dst.width = new_cols; dst.height = new_rows;
     dst.px.resize((size_t)new_cols * new_rows);
     const double sx = (double)src.width / new_cols, sy = (double)src.height / new_rows;
@@ -249,7 +251,7 @@ void PatchMatchCUDA::PatchMatchInit(std::vector<Scene>& Scenes, int ID) {
             cam.K[4] *= scale_y; cam.K[5] *= scale_y;
         }
         cam.width = sc.image.width; cam.height = sc.image.height;
-        images_.push_back(sc.image);
+        images_.push_back(&sc.image);
         cameras_.push_back(cam);
     }
     depth_min_ = cameras_[0].depth_min * 0.6f;      // PatchMatch.cpp:929-930
@@ -266,9 +268,17 @@ void PatchMatchCUDA::PatchMatchInit(std::vector<Scene>& Scenes, int ID) {
 }
 
 void PatchMatchCUDA::CudaMemInit(Scene&) {
-    std::vector<const float*> img(images_.size());
-    for (size_t i = 0; i < images_.size(); ++i) img[i] = images_[i].px.data();
-    check(mpmvs_set_views(h_, (int)images_.size(), img.data(), cameras_.data()), "mpmvs_set_views");
+    bool all_u8 = tex_format_ == MPMVS_TEX_U8;
+    for (const GrayImage* im : images_) all_u8 = all_u8 && im->u8.size() == im->px.size();
+    if (all_u8) {                                   // un-resized 8-bit images: a quarter of the upload, no conversion
+        std::vector<const uint8_t*> img(images_.size());
+        for (size_t i = 0; i < images_.size(); ++i) img[i] = images_[i]->u8.data();
+        check(mpmvs_set_views_u8(h_, (int)images_.size(), img.data(), cameras_.data()), "mpmvs_set_views_u8");
+    } else {
+        std::vector<const float*> img(images_.size());
+        for (size_t i = 0; i < images_.size(); ++i) img[i] = images_[i]->px.data();
+        check(mpmvs_set_views(h_, (int)images_.size(), img.data(), cameras_.data()), "mpmvs_set_views");
+    }
     const size_t wh = (size_t)cameras_[0].width * cameras_[0].height;
     planes_.resize(wh); costs_.resize(wh); geom_costs_.assign(wh, 0.f);
     if (geom_) {

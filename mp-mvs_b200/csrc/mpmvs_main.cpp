@@ -195,9 +195,13 @@ int main(int argc, char* argv[]) {
         const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
         printf("cost time is %.10f us\n", us);
         if (fusion) {
+            const auto f0 = std::chrono::steady_clock::now();
             const size_t npts = RunFusion(config, Scenes);
+            const double fus = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - f0).count();
+            printf("fusion time is %.10f us (host, 1 thread)\n", fus);
             std::cout << "store 3D points to ply file: " << npts << " points" << std::endl;
         }
+        PatchMatchCUDA::ReleasePool();
     } catch (const std::exception& e) {
         std::cout << e.what() << std::endl;
         return EXIT_FAILURE;
