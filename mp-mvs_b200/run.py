@@ -1,0 +1,118 @@
+"""Multi-GPU drop-in for the reference's entry point (main(), /root/reference/src/main.cpp) over a dense folder:
+
+    python mp-mvs_b200/run.py config.yaml [--seed N]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29500 mp-mvs_b200/run.py config.yaml
+
+Reads the same config.yaml keys, `images/%08d.jpg` (or the decoded `.pgm` sidecar), `cams/%08d_cam.txt` and `pair.txt`, runs
+stage 1 and the geometric-consistency iterations sharded by reference image (pipeline.DensePipeline) and writes
+`<Output-folder>/MPMVS/2333_%08d/{depths,normals,costs}.dmb` with background writer threads. Fusion stays with the C++ host
+(mp-mvs_b200/mpmvs_main --fusion-only is not needed: the files are the reference's).
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import pkgload  # noqa: E402
+
+pkgload.load_package()
+from mpmvs_b200 import io_formats, pipeline  # noqa: E402
+
+
+def load_image(folder: str, image_id: int, max_size: int):
+    """PatchMatchInit's loading rule (PatchMatch.cpp:871-925): grey uint8 -> float32, cv::resize(INTER_LINEAR) above
+    `max_size`. Returns (image, scale_x, scale_y); the image stays uint8 when it was not resized."""
+    import cv2
+
+    pgm = os.path.join(folder, f"{image_id:08d}.pgm")
+    img = cv2.imread(pgm if os.path.exists(pgm) else os.path.join(folder, f"{image_id:08d}.jpg"), cv2.IMREAD_GRAYSCALE)
+    if img is None:
+        raise FileNotFoundError(f"Can not read this image ! {image_id:08d}")
+    h, w = img.shape
+    if w <= max_size and h <= max_size:
+        return img, 1.0, 1.0
+    factor = min(np.float32(max_size) / np.float32(w), np.float32(max_size) / np.float32(h))
+    nw, nh = int(round(float(np.float32(w) * factor))), int(round(float(np.float32(h) * factor)))
+    out = cv2.resize(img.astype(np.float32), (nw, nh), interpolation=cv2.INTER_LINEAR)
+    return out, nw / np.float32(w), nh / np.float32(h)
+
+
+def load_scene(cfg: dict, rank: int, world: int):
+    inp = cfg["Input-folder"].rstrip("/")
+    entries = io_formats.read_pairs(os.path.join(inp, "pair.txt"), int(cfg["Max source images num"]))
+    refs = sorted(e.ref_id for e in entries if e.estimate)
+    mine = pipeline.shard_refs(refs, rank, world)
+    by_ref = {e.ref_id: e for e in entries if e.estimate}
+    need = sorted({i for r in mine for i in by_ref[r].src_ids[: 1 + int(cfg["Max source images num"])]} | set(refs[:1]))
+    cams, images = {}, {}
+    for i in sorted(set(refs) | set(need)):
+        cam = io_formats.read_cam(os.path.join(inp, "cams", f"{i:08d}_cam.txt"))
+        if i in need:
+            img, sx, sy = load_image(os.path.join(inp, "images"), i, int(cfg["Max image size"]))
+            images[i] = img
+            cam.K = cam.K.copy()
+            cam.K[0, 0] *= sx; cam.K[0, 2] *= sx; cam.K[1, 1] *= sy; cam.K[1, 2] *= sy
+            cam.height, cam.width = img.shape
+        cams[i] = cam
+    # cameras of images this rank does not load still need a size for the gather buffer: all views share one size
+    h0, w0 = images[need[0]].shape
+    for c in cams.values():
+        if not c.width:
+            c.height, c.width = h0, w0
+    return entries, cams, images
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("config")
+    ap.add_argument("--seed", type=int, default=0x2333)
+    ap.add_argument("--in-flight", type=int, default=4)
+    args = ap.parse_args()
+    import torch
+
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg = io_formats.read_config(args.config)
+    t0 = time.time()
+    entries, cams, images = load_scene(cfg, rank, world)
+    from mpmvs_b200 import capi
+
+    resized = any(im.dtype != np.uint8 for im in images.values())
+    pcfg = pipeline.PipelineConfig(geom_iterations=int(cfg["Geometric consistency iterations"]), max_src=int(cfg["Max source images num"]),
+                                   seed=args.seed, planar_prior=bool(int(cfg["Planer prior"])),
+                                   geom_planar_prior=bool(int(cfg["Geometric consistency planer prior"])),
+                                   tex_format=capi.TEX_F32 if resized else capi.TEX_U8, in_flight=args.in_flight)
+    p = pipeline.DensePipeline(entries, cams, images, pcfg, rank=rank, world=world, device=local, dist=dist)
+    p.setup()
+    t1 = time.time()
+    stats = p.run()
+    torch.cuda.synchronize()
+    t2 = time.time()
+    out = cfg["Output-folder"].rstrip("/")
+    p.write_results(out)
+    t3 = time.time()
+    if dist is not None:
+        dist.barrier()
+    if rank == 0:
+        n = len([e for e in entries if e.estimate])
+        print(f"There are {n} depthmaps; load {t1 - t0:.2f} s, PatchMatch stages {t2 - t1:.2f} s "
+              f"({[(s.name, round(s.device_ms)) for s in stats]}), write {t3 - t2:.2f} s on {world} GPU(s)")
+        print(f"cost time is {(t2 - t1) * 1e6:.10f} us")
+    p.destroy()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

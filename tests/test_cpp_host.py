@@ -82,3 +82,31 @@ def test_main_end_to_end(tmp_path, mode):
         head = f.read(400).decode("latin1")
     nv = int(head.split("element vertex ")[1].split("\n")[0])
     assert nv > 1000
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_size", [3200, 200])
+def test_python_cli_matches_layout(tmp_path, max_size):
+    """mp-mvs_b200/run.py: the sharded pipeline as a drop-in for main() over the same dense folder and YAML keys."""
+    import sys
+
+    sc, root, yaml = write_scene(tmp_path, **{"Geometric consistency iterations": 1, "Planer prior": 1,
+                                              "Geometric consistency planer prior": 0, "Max image size": max_size})
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "mp-mvs_b200", "run.py"), yaml, "--seed", "3"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert "cost time is" in r.stdout
+    scale = 1 if max_size >= 320 else 320 / 200
+    accs = []
+    for i in range(sc.num_views):
+        d = PKG.io_formats.read_dmb(os.path.join(root, "MPMVS", f"2333_{i:08d}", "depths.dmb"))
+        n = PKG.io_formats.read_dmb(os.path.join(root, "MPMVS", f"2333_{i:08d}", "normals.dmb"))
+        assert d.shape == (round(240 / scale), round(320 / scale)) and n.shape == d.shape + (3,)
+        if scale == 1:
+            accs.append(PKG.synth.accuracy_at(d, sc.gt_depth[i])[2])
+        else:
+            import cv2
+
+            gt = cv2.resize(sc.gt_depth[i], (d.shape[1], d.shape[0]), interpolation=cv2.INTER_NEAREST)
+            accs.append(float(100 * (np.abs(d - gt) < 0.05 * gt)[gt > 0].mean()))
+    print("cli accuracy per view", [round(a, 1) for a in accs])
+    assert np.median(accs) > (95 if scale == 1 else 85)
