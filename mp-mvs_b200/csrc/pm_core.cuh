@@ -36,12 +36,6 @@
 #ifndef PM_UNIFORM_VIEWS
 #define PM_UNIFORM_VIEWS 1   // profiles/r01_variant_sweep_*: 5-8 % faster once the cost table is in shared memory
 #endif
-#ifndef PM_VIEW_OUTER
-#define PM_VIEW_OUTER 0  // 1: the 8 propagation candidates are scored view by view (a source view's window stays in L1/TEX)
-#endif
-#ifndef PM_DEBUG_MAXH
-#define PM_DEBUG_MAXH 14   // measurement only: < 14 truncates the hypothesis loop (results are then wrong)
-#endif
 #ifndef PM_EARLY_OUT
 #define PM_EARLY_OUT 1   // stop scoring a refinement proposal once it can no longer be accepted (result-identical)
 #endif
@@ -466,20 +460,8 @@ PM_HD void pm_sweep_pixel(const Ctx& c, const PmFrame& F, const PmState& S, int 
     pm_f4 rand_n = cur, pert_n = cur, base_n = cur, prior_pl = cur;
     bool has_prior = false;
 
-#if PM_VIEW_OUTER
-    // Same 8 x nsrc evaluations as cu:798-819, ordered view-major: all candidates of one source view back to back.
 #pragma unroll 1
-    for (int v = 0; v < nsrc; ++v) {
-#pragma unroll 1
-        for (int h = 0; h < 8; ++h) {
-            if (!((flags >> h) & 1u)) continue;
-            const PmHyp hyp = pm_hyp(F, S.planes[pos[h]], x, y);
-            ca(h, v) = pm_ncc<SCALE>(c, F, st, v, hyp, x, y, nexec);
-        }
-    }
-#endif
-#pragma unroll 1
-    for (int h = PM_VIEW_OUTER ? 8 : 0; h < PM_DEBUG_MAXH; ++h) {
+    for (int h = 0; h < 14; ++h) {
         if (h == 8) {
             // ---- view selection (cu:821-878)
             uint32_t nb[4];  // neighbour masks: up / down / left / right, gated by the flags of regions 0..3 (cu:824-830)

@@ -19,8 +19,6 @@ VARIANTS = {
     "mb2": ["-DPM_MIN_BLOCKS=2"],
     "mb4": ["-DPM_MIN_BLOCKS=4"],
     "mb5": ["-DPM_MIN_BLOCKS=5"],
-    "maxh8": ["-DPM_DEBUG_MAXH=8"],     # measurement only: candidates only
-    "maxh9": ["-DPM_DEBUG_MAXH=9"],     # measurement only: candidates + current plane
     "bh2mb6": ["-DPM_BH=2", "-DPM_MIN_BLOCKS=6"],
     "bh2mb8": ["-DPM_BH=2", "-DPM_MIN_BLOCKS=8"],
     "bh8mb2": ["-DPM_BH=8", "-DPM_MIN_BLOCKS=2"],
