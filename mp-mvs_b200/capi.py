@@ -96,6 +96,11 @@ def lib() -> C.CDLL:
         "mpmvs_ncc_bench": [vp, vp, i, i, i, i, fp, C.POINTER(u64)],
         "mpmvs_uniform_stream": [u64, i, i, i, vp],
         "mpmvs_delaunay": [vp, i, i, i, vp, i, C.POINTER(i)],
+        "mpmvs_fusion_create": [i, i, C.POINTER(vp)],
+        "mpmvs_fusion_destroy": [vp],
+        "mpmvs_fusion_set_view": [vp, i, vp, vp, vp, vp],
+        "mpmvs_fusion_run": [vp, vp, i, i, C.POINTER(u64), fp],
+        "mpmvs_fusion_get_points": [vp, vp, u64],
         "mpmvs_build_prior": [vp, vp],
         "mpmvs_pick_vertices": [vp, i, vp, i, C.POINTER(i)],
         "mpmvs_prior_from_triangles": [vp, vp, i, vp, i, C.POINTER(i)],
@@ -134,6 +139,50 @@ def delaunay(xy: np.ndarray, width: int, height: int) -> np.ndarray:
     n = C.c_int()
     _ck(lib().mpmvs_delaunay(pts.ctypes.data, len(pts), width, height, out.ctypes.data, len(out), C.byref(n)), "delaunay")
     return out[: n.value].copy()
+
+
+class Fusion:
+    """Depth-map fusion of a whole scene on one GPU (mpmvs_fusion_*; RunFusion, PatchMatch.cpp:287-504)."""
+
+    def __init__(self, device: int, n_images: int):
+        self.h = C.c_void_p()
+        self.n = n_images
+        _ck(lib().mpmvs_fusion_create(device, n_images, C.byref(self.h)), "fusion_create")
+
+    def set_view(self, index: int, cam_packed: np.ndarray, depth, normal, gray):
+        d = np.ascontiguousarray(depth, np.float32)
+        nrm = np.ascontiguousarray(normal, np.float32)
+        g = np.ascontiguousarray(gray, np.uint8)
+        cam = np.ascontiguousarray(cam_packed)
+        assert nrm.shape == d.shape + (3,) and g.shape == d.shape
+        _ck(lib().mpmvs_fusion_set_view(self.h, index, cam.ctypes.data, d.ctypes.data, nrm.ctypes.data, g.ctypes.data), "fusion_set_view")
+
+    def run(self, src_lists, use_dynamic_consistency: bool = True):
+        """src_lists: per image [ref, sources...] (None = not estimated). Returns (points (n, 9) float32, device ms)."""
+        width = max(len(r) for r in src_lists if r is not None) + 1
+        tab = np.full((self.n, width), -2, np.int32)
+        for k, r in enumerate(src_lists):
+            if r is None:
+                tab[k, 0] = -1
+            else:
+                tab[k, : len(r)] = r
+        n, ms = C.c_uint64(), C.c_float()
+        _ck(lib().mpmvs_fusion_run(self.h, tab.ctypes.data, width, int(use_dynamic_consistency), C.byref(n), C.byref(ms)), "fusion_run")
+        pts = np.empty((int(n.value), 9), np.float32)
+        if len(pts):
+            _ck(lib().mpmvs_fusion_get_points(self.h, pts.ctypes.data, len(pts)), "fusion_get_points")
+        return pts, float(ms.value)
+
+    def destroy(self):
+        if self.h:
+            lib().mpmvs_fusion_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
 
 
 class ImageCache:

@@ -2,11 +2,12 @@
 // config.yaml -> pair.txt -> stage 1 (multi-scale photometric [+ planar prior]) -> geometric-consistency iterations
 // [+ planar prior] -> fusion -> MPMVS_model.ply, on the same dense-folder layout and with the same output files.
 //
-//   mpmvs_main [config.yaml] [--seed N] [--tex f32|u8] [--no-fusion]
+//   mpmvs_main [config.yaml] [--seed N] [--tex f32|u8] [--no-fusion] [--gpu-fusion]
 //
 // The reference bakes the config path in at cmake time (include/ProjectPath.h.in) and takes no arguments.
 #include <sys/stat.h>
 
+#include <algorithm>
 #include <cfloat>
 #include <chrono>
 #include <cstdlib>
@@ -158,6 +159,51 @@ size_t RunFusion(const ConfigParams& config, std::vector<Scene>& Scenes) {
     return cloud.size();
 }
 
+// The same stage on the GPU (mpmvs_fusion_*, pm_fusion.cu): images in the reference's order, the pixels of one image in
+// parallel. Selected with --gpu-fusion; the sequential host loop above stays the default because it is the reference's
+// exact order.
+size_t RunFusionGPU(const ConfigParams& config, std::vector<Scene>& Scenes) {
+    const int n = (int)Scenes.size();
+    mpmvs_fusion* f = nullptr;
+    check(mpmvs_fusion_create(0, n, &f), "mpmvs_fusion_create");
+    const std::string image_folder = config.input_folder + "/images", cam_folder = config.input_folder + "/cams";
+    int max_list = 2;
+    for (const Scene& s : Scenes) max_list = std::max(max_list, (int)s.srcID.size() + 1);
+    std::vector<int> lists((size_t)n * max_list, -2);
+    for (int i = 0; i < n; ++i) {
+        if (!Scenes[i].estimate) { lists[(size_t)i * max_list] = -1; continue; }
+        const int id = Scenes[i].refID;
+        Camera cam = ReadCamera(cam_folder + "/" + id8(id) + "_cam.txt");
+        const std::string folder = config.input_folder + "/MPMVS/2333_" + id8(id);
+        int h, w, nb;
+        std::vector<float> depth, normal;
+        if (!readDmb(folder + "/depths.dmb", h, w, nb, depth) || !readDmb(folder + "/normals.dmb", h, w, nb, normal))
+            throw std::runtime_error("fusion: missing results in " + folder);
+        if (Scenes[i].image.empty() && !readGrayImage(image_folder, id, Scenes[i].image)) throw std::runtime_error("fusion: missing image " + id8(id));
+        GrayImage im = Scenes[i].image;
+        const int ow = Scenes[i].orig_width ? Scenes[i].orig_width : im.width, oh = Scenes[i].orig_height ? Scenes[i].orig_height : im.height;
+        if (im.width != w || im.height != h) im = resizeLinear(im, w, h);
+        if (ow != w || oh != h) { cam.K[0] *= w / (float)ow; cam.K[2] *= w / (float)ow; cam.K[4] *= h / (float)oh; cam.K[5] *= h / (float)oh; }
+        cam.width = w; cam.height = h;
+        std::vector<unsigned char> gray(im.px.size());
+        for (size_t k = 0; k < gray.size(); ++k) gray[k] = (unsigned char)std::min(255.f, std::max(0.f, std::round(im.px[k])));
+        check(mpmvs_fusion_set_view(f, i, &cam, depth.data(), normal.data(), gray.data()), "mpmvs_fusion_set_view");
+        for (size_t j = 0; j < Scenes[i].srcID.size(); ++j) {
+            const int s = Scenes[i].srcID[j];
+            lists[(size_t)i * max_list + j] = (s >= 0 && s < n && Scenes[s].estimate) ? s : -1;
+        }
+    }
+    uint64_t npts = 0;
+    float ms = 0.f;
+    check(mpmvs_fusion_run(f, lists.data(), max_list, config.use_dynamic_consistency ? 1 : 0, &npts, &ms), "mpmvs_fusion_run");
+    std::vector<PointList> cloud(npts);
+    if (npts) check(mpmvs_fusion_get_points(f, (float*)cloud.data(), npts), "mpmvs_fusion_get_points");
+    mpmvs_fusion_destroy(f);
+    printf("GPU fusion kernels: %.3f ms\n", ms);
+    StoreColorPlyFileBinaryPointCloud(config.output_folder + "/MPMVS_model.ply", cloud);
+    return cloud.size();
+}
+
 }  // namespace mpmvs
 
 int main(int argc, char* argv[]) {
@@ -165,11 +211,12 @@ int main(int argc, char* argv[]) {
     std::string yaml = "config/config.yaml";
     uint64_t seed = 0x2333;
     int tex = MPMVS_TEX_F32;
-    bool fusion = true;
+    bool fusion = true, gpu_fusion = false;
     for (int i = 1; i < argc; ++i) {
         if (!strcmp(argv[i], "--seed") && i + 1 < argc) seed = strtoull(argv[++i], nullptr, 0);
         else if (!strcmp(argv[i], "--tex") && i + 1 < argc) tex = !strcmp(argv[++i], "u8") ? MPMVS_TEX_U8 : MPMVS_TEX_F32;
         else if (!strcmp(argv[i], "--no-fusion")) fusion = false;
+        else if (!strcmp(argv[i], "--gpu-fusion")) gpu_fusion = true;
         else yaml = argv[i];
     }
     try {
@@ -196,9 +243,9 @@ int main(int argc, char* argv[]) {
         printf("cost time is %.10f us\n", us);
         if (fusion) {
             const auto f0 = std::chrono::steady_clock::now();
-            const size_t npts = RunFusion(config, Scenes);
+            const size_t npts = gpu_fusion ? RunFusionGPU(config, Scenes) : RunFusion(config, Scenes);
             const double fus = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - f0).count();
-            printf("fusion time is %.10f us (host, 1 thread)\n", fus);
+            printf("fusion time is %.10f us (%s)\n", fus, gpu_fusion ? "GPU kernels + file I/O" : "host, 1 thread");
             std::cout << "store 3D points to ply file: " << npts << " points" << std::endl;
         }
         PatchMatchCUDA::ReleasePool();

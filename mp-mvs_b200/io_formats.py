@@ -246,3 +246,19 @@ def read_config(path: str) -> dict:
 def result_dir(out_folder: str, ref_id: int) -> str:
     """<Output-folder>/MPMVS/2333_%08d (PatchMatch.cpp:510-513, utility.cpp:30)."""
     return os.path.join(out_folder, "MPMVS", f"2333_{ref_id:08d}")
+
+
+def write_ply(path: str, points9: np.ndarray) -> None:
+    """StoreColorPlyFileBinaryPointCloud, PatchMatch.cpp:145-198: binary little-endian x y z nx ny nz + uchar r g b.
+    points9: (n, 9) float32 = coord, normal, colour (b, g, r as in PointList::color)."""
+    p = np.asarray(points9, dtype=np.float32).reshape(-1, 9)
+    rec = np.zeros(len(p), dtype=[("xyz", "<f4", 3), ("n", "<f4", 3), ("rgb", "u1", 3)])
+    xyz = p[:, :3].copy()
+    xyz[~np.isfinite(xyz).all(1)] = 0.0                      # :175-179
+    rec["xyz"], rec["n"] = xyz, p[:, 3:6]
+    rec["rgb"] = np.clip(p[:, [8, 7, 6]], 0, 255).astype(np.int32).astype(np.uint8)
+    with open(path, "wb") as f:
+        f.write(("ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n"
+                 "property float nx\nproperty float ny\nproperty float nz\nproperty uchar red\nproperty uchar green\nproperty uchar blue\n"
+                 "end_header\n" % len(p)).encode())
+        rec.tofile(f)

@@ -73,6 +73,7 @@ def main():
     ap.add_argument("config")
     ap.add_argument("--seed", type=int, default=0x2333)
     ap.add_argument("--in-flight", type=int, default=4)
+    ap.add_argument("--fusion", type=int, default=1, help="fuse the depth maps on rank 0's GPU and write MPMVS_model.ply")
     args = ap.parse_args()
     import torch
 
@@ -104,11 +105,34 @@ def main():
     t3 = time.time()
     if dist is not None:
         dist.barrier()
+    t4 = t3
+    n_points = None
+    if rank == 0 and args.fusion:
+        # RunFusion (PatchMatch.cpp:287-504) on the GPU: every rank has written its maps, rank 0 reads them back
+        est = sorted(e.ref_id for e in entries if e.estimate)
+        by_ref = {e.ref_id: e for e in entries if e.estimate}
+        fz = capi.Fusion(local, max(est) + 1)
+        lists = [None] * (max(est) + 1)
+        for i in est:
+            d = io_formats.read_dmb(os.path.join(io_formats.result_dir(out, i), "depths.dmb"))
+            nrm = io_formats.read_dmb(os.path.join(io_formats.result_dir(out, i), "normals.dmb"))
+            img, _, _ = load_image(os.path.join(cfg["Input-folder"].rstrip("/"), "images"), i, int(cfg["Max image size"]))
+            cam = cams[i]
+            cam.height, cam.width = d.shape
+            fz.set_view(i, io_formats.pack_cameras([cam]), d, nrm, np.clip(np.rint(img), 0, 255).astype(np.uint8))
+            lists[i] = [i] + [j if j in by_ref else -1 for j in by_ref[i].src_ids[1:]]
+        pts, fus_ms = fz.run(lists, bool(int(cfg["Use dynamic_consistency to fuse"])))
+        fz.destroy()
+        io_formats.write_ply(os.path.join(out, "MPMVS", "MPMVS_model.ply"), pts)
+        n_points = len(pts)
+        t4 = time.time()
     if rank == 0:
         n = len([e for e in entries if e.estimate])
         print(f"There are {n} depthmaps; load {t1 - t0:.2f} s, PatchMatch stages {t2 - t1:.2f} s "
               f"({[(s.name, round(s.device_ms)) for s in stats]}), write {t3 - t2:.2f} s on {world} GPU(s)")
         print(f"cost time is {(t2 - t1) * 1e6:.10f} us")
+        if n_points is not None:
+            print(f"fusion: {n_points} points in {t4 - t3:.2f} s (load + GPU fusion + ply)")
     p.destroy()
     if dist is not None:
         dist.destroy_process_group()

@@ -110,3 +110,6 @@ def test_python_cli_matches_layout(tmp_path, max_size):
             accs.append(float(100 * (np.abs(d - gt) < 0.05 * gt)[gt > 0].mean()))
     print("cli accuracy per view", [round(a, 1) for a in accs])
     assert np.median(accs) > (95 if scale == 1 else 85)
+    with open(os.path.join(root, "MPMVS", "MPMVS_model.ply"), "rb") as f:       # fused on the GPU by the driver
+        head = f.read(400).decode("latin1")
+    assert int(head.split("element vertex ")[1].split("\n")[0]) > 1000 and "fusion:" in r.stdout
