@@ -192,11 +192,19 @@ int mpmvs_fusion_run(mpmvs_fusion* f, const int* src_lists, int max_list, int us
         FCK(cudaMalloc((void**)&f->d_points, total * sizeof(FusedPoint)));
         f->cap_points = total;
     }
-    FusedPoint* tmp = nullptr;
-    unsigned char* keep = nullptr;
-    int* d_src = nullptr;
-    size_t* d_num = nullptr;
-    void* d_cub = nullptr;
+    struct Temps {                       // freed on every return path
+        FusedPoint* tmp = nullptr;
+        unsigned char* keep = nullptr;
+        int* d_src = nullptr;
+        size_t* d_num = nullptr;
+        void* d_cub = nullptr;
+        ~Temps() { cudaFree(tmp); cudaFree(keep); cudaFree(d_src); cudaFree(d_num); cudaFree(d_cub); }
+    } T;
+    FusedPoint*& tmp = T.tmp;
+    unsigned char*& keep = T.keep;
+    int*& d_src = T.d_src;
+    size_t*& d_num = T.d_num;
+    void*& d_cub = T.d_cub;
     size_t cub_bytes = 0;
     FCK(cudaMalloc((void**)&tmp, max_wh * sizeof(FusedPoint)));
     FCK(cudaMalloc((void**)&keep, max_wh));
@@ -236,7 +244,6 @@ int mpmvs_fusion_run(mpmvs_fusion* f, const int* src_lists, int max_list, int us
     float t = 0.f;
     cudaEventElapsedTime(&t, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cudaFree(tmp); cudaFree(keep); cudaFree(d_src); cudaFree(d_num); cudaFree(d_cub);
     if (rc) return rc;
     FCK(cudaGetLastError());
     if (n_points) *n_points = f->n_points;
