@@ -49,7 +49,7 @@ struct Scene {                                     // utility.h:17-26
     std::vector<int> srcID;
     GrayImage image;                                // decoded (and, above max_image_size, resized) grey image, cached
     int orig_width = 0, orig_height = 0;            // size of the file on disk (K is scaled by image size / this)
-    std::vector<float> depth;
+    std::vector<float> depth, normal, cost;         // latest results of this image (what its .dmb files hold), kept in memory
     int max_image_size = 3200;
 };
 struct ConfigParams {                              // utility.h:28-46

@@ -258,16 +258,18 @@ void PatchMatchCUDA::PatchMatchInit(std::vector<Scene>& Scenes, int ID) {
     depth_max_ = cameras_[0].depth_max * 1.2f;
     if (geom_) {                                    // PatchMatch.cpp:933-950: the sources' depth maps of the previous pass
         for (size_t i = 1; i < srcID.size(); ++i) {
+            const size_t wh = (size_t)cameras_[i].width * cameras_[i].height;
+            const Scene& src = Scenes[srcID[i]];
+            if (src.depth.size() == wh) { depths_.push_back(src.depth); continue; }   // this process wrote that file itself
             int h, w, nb;
             std::vector<float> d;
-            if (!readDmb(input_folder_ + "/MPMVS/2333_" + id8(srcID[i]) + "/depths.dmb", h, w, nb, d))
-                d.assign((size_t)cameras_[i].width * cameras_[i].height, 0.f);
+            if (!readDmb(input_folder_ + "/MPMVS/2333_" + id8(srcID[i]) + "/depths.dmb", h, w, nb, d)) d.assign(wh, 0.f);
             depths_.push_back(std::move(d));
         }
     }
 }
 
-void PatchMatchCUDA::CudaMemInit(Scene&) {
+void PatchMatchCUDA::CudaMemInit(Scene& scene) {
     bool all_u8 = tex_format_ == MPMVS_TEX_U8;
     for (const GrayImage* im : images_) all_u8 = all_u8 && im->u8.size() == im->px.size();
     if (all_u8) {                                   // un-resized 8-bit images: a quarter of the upload, no conversion
@@ -289,9 +291,12 @@ void PatchMatchCUDA::CudaMemInit(Scene&) {
         const std::string folder = input_folder_ + "/MPMVS/2333_" + id8(ref_id_);
         int h, w, nb;
         std::vector<float> d, n, c;
-        if (!readDmb(folder + "/depths.dmb", h, w, nb, d) || !readDmb(folder + "/normals.dmb", h, w, nb, n) ||
-            !readDmb(folder + "/costs.dmb", h, w, nb, c) || d.size() != wh)
+        if (scene.depth.size() == wh && scene.normal.size() == 3 * wh && scene.cost.size() == wh) {
+            d = scene.depth; n = scene.normal; c = scene.cost;      // written by this process in the previous pass
+        } else if (!readDmb(folder + "/depths.dmb", h, w, nb, d) || !readDmb(folder + "/normals.dmb", h, w, nb, n) ||
+                   !readDmb(folder + "/costs.dmb", h, w, nb, c) || d.size() != wh) {
             throw std::runtime_error("geometric consistency pass needs the previous results in " + folder);
+        }
         for (size_t i = 0; i < wh; ++i) { planes_[i] = {n[3 * i], n[3 * i + 1], n[3 * i + 2], d[i]}; costs_[i] = c[i]; }
         check(mpmvs_set_state(h_, (const float*)planes_.data(), costs_.data()), "mpmvs_set_state");
     }
@@ -391,6 +396,9 @@ void ProcessProblem(const std::string& input_folder, const std::string& output_f
     writeDmb(result_folder + "/depths.dmb", height, width, 1, depths.data());
     writeDmb(result_folder + "/normals.dmb", height, width, 3, normals.data());
     writeDmb(result_folder + "/costs.dmb", height, width, 1, MP.costs().data());
+    scene.depth = std::move(depths);            // later passes (and other images of this pass: the reference's in-place,
+    scene.normal = std::move(normals);          // Gauss-Seidel order) read these instead of the files
+    scene.cost = MP.costs();
     std::cout << "Processing image " << id8(scene.refID) << " done!" << std::endl;
     MP.Release(Scenes, ID);
 }
