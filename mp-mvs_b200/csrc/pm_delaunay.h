@@ -3,10 +3,12 @@
 // Replaces cv::Subdiv2D in PatchMatchCUDA::DelaunayTriangulation (/root/reference/src/PatchMatch.cpp:757-780), which
 // OpenCV-free builds cannot call. Vertices are pixel positions (one per 5x5 cell, GetTriangulateVertices :782-853), so
 // all predicates are evaluated exactly in 64/128-bit integers: no epsilons, no robustness fallbacks. Points are
-// inserted in the given order (row-major cells -> short walks) with Lawson flips. The triangulation of co-circular
+// inserted band by band in boustrophedon order (short walks whatever the caller's order) with Lawson flips. The triangulation of co-circular
 // point sets is not unique (common on a pixel grid); like OpenCV's, the result is then ONE valid Delaunay triangulation.
 #ifndef MPMVS_PM_DELAUNAY_H
 #define MPMVS_PM_DELAUNAY_H
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <vector>
 
@@ -38,7 +40,26 @@ class Delaunay {
         t.n[0] = t.n[1] = t.n[2] = -1;
         tris_.push_back(t);
         last_ = 0;
-        for (int i = 0; i < n; ++i) insert(i);
+        // Insertion order: bands of rows walked boustrophedon, so that every point is located by a short walk from the
+        // previous one whatever order the caller used (a random order would make the walks O(sqrt n) each).
+        const int band = n > 0 ? (int)std::max(1.0, std::sqrt((double)width * height / n)) : 1;
+        const int n_bands = height / band + 1;
+        std::vector<int> start((size_t)n_bands + 1, 0), order((size_t)n);
+        for (int i = 0; i < n; ++i) ++start[xy[2 * i + 1] / band + 1];
+        for (int b = 0; b < n_bands; ++b) start[b + 1] += start[b];
+        {
+            std::vector<int> fill(start.begin(), start.end() - 1);
+            for (int i = 0; i < n; ++i) order[fill[xy[2 * i + 1] / band]++] = i;     // counting sort by band (stable)
+        }
+        for (int b = 0; b < n_bands; ++b) {                                          // then by x, alternating direction
+            const bool rev = b & 1;
+            std::sort(order.begin() + start[b], order.begin() + start[b + 1], [&](int p, int q) {
+                const int xp = xy[2 * p], xq = xy[2 * q];
+                if (xp != xq) return rev ? xp > xq : xp < xq;
+                return xy[2 * p + 1] != xy[2 * q + 1] ? xy[2 * p + 1] < xy[2 * q + 1] : p < q;
+            });
+        }
+        for (int i = 0; i < n; ++i) insert(order[i]);
     }
 
     // triangles whose three vertices are input points, as vertex indices
