@@ -13,9 +13,11 @@
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
 
 // pattern: 0 = row strip (lane i -> x+i, same row), 1 = checkerboard (lane i -> x+i, row + (i&1)), 2 = 8x4 block
+// lane_mask: which lanes of every warp take part (0xffffffff = all). Idle lanes skip the fetches (divergent branch), as
+// lanes of the PatchMatch kernel do when their pixel does not need the view being scored.
 template <int PATTERN, int STEP>
 __global__ void __launch_bounds__(256) fetch_kernel(cudaTextureObject_t tex, int W, int H, int layers, float jitter, int reps, float scale,
-                                                    float* out) {
+                                                    float* out, unsigned lane_mask = 0xffffffffu) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int px, py;
     if (PATTERN == 0) { px = lane; py = 0; }
@@ -27,6 +29,7 @@ __global__ void __launch_bounds__(256) fetch_kernel(cudaTextureObject_t tex, int
     const float jx = ((h >> 8) & 1023) * (1.0f / 1023.0f) * jitter, jy = ((h >> 18) & 1023) * (1.0f / 1023.0f) * jitter;
     float acc = 0.f;
     float fx = bx + px * scale + jx + 0.37f, fy = by + py * scale + jy + 0.61f;
+    if (!((lane_mask >> lane) & 1u)) return;
     for (int r = 0; r < reps; ++r) {
         const int layer = r % layers;
 #pragma unroll
@@ -111,6 +114,25 @@ int main() {
         }
         run<1, 2>(f.name, f.tex, W, H, L, 0.0f, 0.5f, dout, clock_khz, sms);   // minified source (texels shared by neighbours)
         run<1, 2>(f.name, f.tex, W, H, L, 0.0f, 2.0f, dout, clock_khz, sms);   // magnified 2x (sparser footprint)
+    }
+    // partially active warps: is the unit's cost per warp instruction or per active quad / lane?
+    struct M { const char* name; unsigned mask; int lanes; };
+    const M masks[] = {{"all 32 lanes", 0xffffffffu, 32}, {"lanes 0-15 (4 full quads)", 0x0000ffffu, 16}, {"every other quad (4 full quads)", 0x0f0f0f0fu, 16},
+                       {"2 lanes of every quad", 0x33333333u, 16}, {"26 lanes (6 full quads + 2 lanes)", 0x03ffffffu, 26}, {"3 lanes of every quad", 0x77777777u, 24}};
+    for (const M& m : masks) {
+        const int blocks = sms * 24, reps = 64;
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        fetch_kernel<1, 2><<<blocks, 256>>>(fmts[3].tex, W, H, L, 0.f, 4, 1.0f, dout, m.mask);
+        cudaEventRecord(e0);
+        fetch_kernel<1, 2><<<blocks, 256>>>(fmts[3].tex, W, H, L, 0.f, reps, 1.0f, dout, m.mask);
+        cudaEventRecord(e1);
+        CK(cudaEventSynchronize(e1));
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double taps = (double)blocks * 8 * m.lanes * reps * 36;
+        printf("u8 unorm linear, %-36s : %8.3f ms  %7.1f Gtaps/s  %.3f taps/clk/SM  (%.3f warp-instr/clk/SM x 8)\n", m.name, ms, taps / ms / 1e6,
+               taps / (ms * 1e-3) / (clock_khz * 1e3) / sms, (double)blocks * 8 * reps * 36 / (ms * 1e-3) / (clock_khz * 1e3) / sms * 8);
     }
     return 0;
 }
