@@ -12,6 +12,8 @@ fmts = sys.argv[3].split(",") if len(sys.argv) > 3 else ["f32", "f16", "u8"]
 for v in variants:
     for f in fmts:
         env = dict(os.environ, MPMVS_LIB_VARIANT=v)
+        if v == "default" and not os.path.exists(os.path.join(ROOT, "mp-mvs_b200", "variants", "libmpmvs_b200_default.so")):
+            env.pop("MPMVS_LIB_VARIANT")          # the in-tree library
         r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", workload, "--steps", "2", "--warmup", "1",
                             "--no-cpu-baseline", "--tex", f], env=env, capture_output=True, text=True)
         try:
