@@ -101,6 +101,8 @@ def lib() -> C.CDLL:
         "mpmvs_fusion_set_view": [vp, i, vp, vp, vp, vp],
         "mpmvs_fusion_run": [vp, vp, i, i, C.POINTER(u64), fp],
         "mpmvs_fusion_get_points": [vp, vp, u64],
+        "mpmvs_fusion_set_sky_mask": [vp, i, vp],
+        "mpmvs_sky_mask_refine": [i, vp, vp, i, i, vp, i, i, vp, vp, fp],
         "mpmvs_build_prior": [vp, vp],
         "mpmvs_pick_vertices": [vp, i, vp, i, C.POINTER(i)],
         "mpmvs_prior_from_triangles": [vp, vp, i, vp, i, C.POINTER(i)],
@@ -141,6 +143,22 @@ def delaunay(xy: np.ndarray, width: int, height: int) -> np.ndarray:
     return out[: n.value].copy()
 
 
+def sky_mask_refine(bgr, mask, device: int = 0, stream: int | None = None, want_prob: bool = False):
+    """bilateral_filter() of GenerateSkyRegionMask (SkySegment/src/SkyRegionDetect.cu:3-66): joint-bilateral upsampling of a
+    sky probability map `mask` (float, any size) guided by the colour image `bgr` ([h][w][3] uint8).
+    Returns (result [h][w] float32 of 0 / 255, prob or None, device ms)."""
+    img = np.ascontiguousarray(bgr, np.uint8)
+    m = np.ascontiguousarray(mask, np.float32)
+    assert img.ndim == 3 and img.shape[2] == 3 and m.ndim == 2
+    h, w = img.shape[:2]
+    out = np.empty((h, w), np.float32)
+    prob = np.empty((h, w), np.float32) if want_prob else None
+    ms = C.c_float()
+    _ck(lib().mpmvs_sky_mask_refine(device, C.c_void_p(stream) if stream else None, img.ctypes.data, w, h, m.ctypes.data, m.shape[1],
+                                    m.shape[0], out.ctypes.data, prob.ctypes.data if want_prob else None, C.byref(ms)), "sky_mask_refine")
+    return out, prob, float(ms.value)
+
+
 class Fusion:
     """Depth-map fusion of a whole scene on one GPU (mpmvs_fusion_*; RunFusion, PatchMatch.cpp:287-504)."""
 
@@ -156,6 +174,11 @@ class Fusion:
         cam = np.ascontiguousarray(cam_packed)
         assert nrm.shape == d.shape + (3,) and g.shape == d.shape
         _ck(lib().mpmvs_fusion_set_view(self.h, index, cam.ctypes.data, d.ctypes.data, nrm.ctypes.data, g.ctypes.data), "fusion_set_view")
+
+    def set_sky_mask(self, index: int, sky):
+        """sky [h][w] uint8, > 0 = sky (skymask_refine.jpg): masked when that view's turn comes (PatchMatch.cpp:385-388)."""
+        m = np.ascontiguousarray(sky, np.uint8)
+        _ck(lib().mpmvs_fusion_set_sky_mask(self.h, index, m.ctypes.data), "fusion_set_sky_mask")
 
     def run(self, src_lists, use_dynamic_consistency: bool = True):
         """src_lists: per image [ref, sources...] (None = not estimated). Returns (points (n, 9) float32, device ms)."""

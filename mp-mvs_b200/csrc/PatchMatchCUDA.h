@@ -72,7 +72,12 @@ Camera ReadCamera(const std::string& cam_path);                                 
 bool readDmb(const std::string& path, int& h, int& w, int& nb, std::vector<float>& data);   // utility.cpp:193-217,251-280
 bool writeDmb(const std::string& path, int h, int w, int nb, const float* data);            // utility.cpp:219-248,282-308
 bool readGrayImage(const std::string& image_folder, int id, GrayImage& out);    // %08d.pgm (decoded sidecar) or %08d.jpg (nvJPEG)
+bool readGrayFile(const std::string& path_without_ext, GrayImage& out);        // <path>.pgm or <path>.jpg (nvJPEG luma)
+bool readColorFile(const std::string& path_without_ext, int& w, int& h, std::vector<unsigned char>& bgr);   // .ppm or .jpg, B G R interleaved
+bool writePgm(const std::string& path, int w, int h, const unsigned char* px);
 GrayImage resizeLinear(const GrayImage& src, int new_cols, int new_rows);       // cv::resize(..., INTER_LINEAR) on float
+int GenerateSkyRegionMask(std::vector<Scene>& Scenes, const ConfigParams& config);   // PatchMatch.cpp:4-57 minus the network
+std::vector<unsigned char> readSkyMask(const std::string& result_folder, int w, int h);   // PatchMatch.cpp:358-373
 
 // ------------------------------------------------------------------------------------------------ the class
 class PatchMatchCUDA {

@@ -184,12 +184,121 @@ static bool readJpegLuma(const std::string& path, GrayImage& out) {
 }
 #endif
 
-bool readGrayImage(const std::string& image_folder, int id, GrayImage& out) {
-    if (readPgm(image_folder + "/" + id8(id) + ".pgm", out)) return true;
+bool readGrayFile(const std::string& path_without_ext, GrayImage& out) {
+    if (readPgm(path_without_ext + ".pgm", out)) return true;
 #ifdef MPMVS_WITH_NVJPEG
-    if (readJpegLuma(image_folder + "/" + id8(id) + ".jpg", out)) return true;
+    if (readJpegLuma(path_without_ext + ".jpg", out)) return true;
 #endif
     return false;
+}
+
+bool readGrayImage(const std::string& image_folder, int id, GrayImage& out) { return readGrayFile(image_folder + "/" + id8(id), out); }
+
+bool writePgm(const std::string& path, int w, int h, const unsigned char* px) {
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    fprintf(f, "P5\n%d %d\n255\n", w, h);
+    const bool ok = fwrite(px, 1, (size_t)w * h, f) == (size_t)w * h;
+    fclose(f);
+    return ok;
+}
+
+// cv::imread(path, 1): interleaved B, G, R. Sources: a binary PPM sidecar (R, G, B on disk) or the JPEG through nvJPEG.
+bool readColorFile(const std::string& path_without_ext, int& w, int& h, std::vector<unsigned char>& bgr) {
+    {
+        std::ifstream f(path_without_ext + ".ppm", std::ios::binary);
+        std::string magic;
+        int maxv = 0;
+        if (f.is_open() && (f >> magic >> w >> h >> maxv) && magic == "P6" && maxv == 255 && w > 0 && h > 0) {
+            f.get();
+            bgr.resize((size_t)w * h * 3);
+            f.read((char*)bgr.data(), bgr.size());
+            if ((size_t)f.gcount() == bgr.size()) {
+                for (size_t i = 0; i < bgr.size(); i += 3) std::swap(bgr[i], bgr[i + 2]);
+                return true;
+            }
+        }
+    }
+#ifdef MPMVS_WITH_NVJPEG
+    std::ifstream f(path_without_ext + ".jpg", std::ios::binary);
+    if (!f.is_open()) return false;
+    std::vector<unsigned char> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    nvjpegHandle_t handle = nullptr;
+    nvjpegJpegState_t state = nullptr;
+    if (nvjpegCreateSimple(&handle) != NVJPEG_STATUS_SUCCESS) return false;
+    if (nvjpegJpegStateCreate(handle, &state) != NVJPEG_STATUS_SUCCESS) { nvjpegDestroy(handle); return false; }
+    int comps = 0, ws[NVJPEG_MAX_COMPONENT], hs[NVJPEG_MAX_COMPONENT];
+    nvjpegChromaSubsampling_t ss;
+    bool ok = nvjpegGetImageInfo(handle, bytes.data(), bytes.size(), &comps, &ss, ws, hs) == NVJPEG_STATUS_SUCCESS;
+    nvjpegImage_t img{};
+    const bool grey = ok && comps == 1;            // a single-component JPEG: cv::imread(path, 1) replicates the luma plane
+    if (ok) {
+        w = ws[0]; h = hs[0];
+        ok = cudaMalloc((void**)&img.channel[0], (size_t)w * h * (grey ? 1 : 3)) == cudaSuccess;
+        img.pitch[0] = (size_t)w * (grey ? 1 : 3);
+    }
+    if (ok) ok = nvjpegDecode(handle, state, bytes.data(), bytes.size(), grey ? NVJPEG_OUTPUT_Y : NVJPEG_OUTPUT_BGRI, &img, 0) == NVJPEG_STATUS_SUCCESS;
+    if (ok && grey) {
+        std::vector<unsigned char> y((size_t)w * h);
+        ok = cudaMemcpy(y.data(), img.channel[0], y.size(), cudaMemcpyDeviceToHost) == cudaSuccess;
+        bgr.resize(y.size() * 3);
+        for (size_t i = 0; i < y.size(); ++i) bgr[3 * i] = bgr[3 * i + 1] = bgr[3 * i + 2] = y[i];
+    } else if (ok) {
+        bgr.resize((size_t)w * h * 3);
+        ok = cudaMemcpy(bgr.data(), img.channel[0], bgr.size(), cudaMemcpyDeviceToHost) == cudaSuccess;
+    }
+    cudaFree(img.channel[0]);
+    nvjpegJpegStateDestroy(state);
+    nvjpegDestroy(handle);
+    return ok;
+#else
+    return false;
+#endif
+}
+
+// GenerateSkyRegionMask, PatchMatch.cpp:4-57, without the segmentation network (ncnn): the coarse map it would produce is
+// read from <out>/MPMVS/2333_%08d/skymask.{pgm,jpg} (255 x probability, any size -- the file the reference itself writes at
+// cpp:42-44), refined by joint-bilateral upsampling on the GPU (mpmvs_sky_mask_refine; bilateral_filter, cpp:46-47) and
+// stored as skymask_refine.pgm for RunFusion. Images above `Max image size` would need cv::resize on 8-bit colour
+// (fixed-point arithmetic, not restated here): they are skipped with a message -- mp-mvs_b200/run.py handles them via cv2.
+int GenerateSkyRegionMask(std::vector<Scene>& Scenes, const ConfigParams& config) {
+    int done = 0;
+    for (Scene& sc : Scenes) {
+        if (!sc.estimate) continue;
+        const std::string folder = config.output_folder + "/2333_" + id8(sc.refID);   // output_folder already ends in /MPMVS (readConfig)
+        GrayImage coarse;
+        if (!readGrayFile(folder + "/skymask", coarse)) continue;
+        int w = 0, h = 0;
+        std::vector<unsigned char> bgr;
+        if (!readColorFile(config.input_folder + "/images/" + id8(sc.refID), w, h, bgr)) {
+            std::cout << "Can not read this image ! " << id8(sc.refID) << std::endl;
+            continue;
+        }
+        if (w > config.MaxImageSize || h > config.MaxImageSize) {
+            std::cout << "sky mask of image " << id8(sc.refID) << " skipped: image above Max image size (use mp-mvs_b200/run.py)" << std::endl;
+            continue;
+        }
+        std::vector<float> prob(coarse.px.size()), refined((size_t)w * h);
+        for (size_t i = 0; i < prob.size(); ++i) prob[i] = coarse.px[i] / 255.0f;
+        check(mpmvs_sky_mask_refine(0, nullptr, bgr.data(), w, h, prob.data(), coarse.width, coarse.height, refined.data(), nullptr, nullptr),
+              "mpmvs_sky_mask_refine");
+        std::vector<unsigned char> u8(refined.size());
+        for (size_t i = 0; i < u8.size(); ++i) u8[i] = refined[i] > 0.f ? 255 : 0;       // convertTo(CV_8U), cpp:48-50
+        if (!writePgm(folder + "/skymask_refine.pgm", w, h, u8.data())) throw std::runtime_error("can not write " + folder + "/skymask_refine.pgm");
+        ++done;
+    }
+    return done;
+}
+
+// The sky gate RunFusion reads (PatchMatch.cpp:358-373): skymask_refine brought to the depth map's size; empty = none.
+std::vector<unsigned char> readSkyMask(const std::string& folder, int w, int h) {
+    GrayImage m;
+    std::vector<unsigned char> out;
+    if (!readGrayFile(folder + "/skymask_refine", m)) return out;
+    if (m.width != w || m.height != h) m = resizeLinear(m, w, h);
+    out.resize((size_t)w * h);
+    for (size_t i = 0; i < out.size(); ++i) out[i] = m.px[i] > 0.f ? 255 : 0;
+    return out;
 }
 
 // cv::resize(src, dst, Size(new_cols, new_rows), 0, 0, INTER_LINEAR) for CV_32FC1 (PatchMatch.cpp:915): pixel-centre

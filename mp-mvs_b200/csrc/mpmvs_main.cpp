@@ -58,14 +58,13 @@ static void StoreColorPlyFileBinaryPointCloud(const std::string& path, const std
     fclose(f);
 }
 
-// RunFusion, PatchMatch.cpp:287-504 (host, single thread, pixel order and mask side effects as in the reference; the sky
-// mask branch needs ncnn and is not built). Colour: the grey image replicated to three channels when only the decoded
-// grey sidecar exists.
+// RunFusion, PatchMatch.cpp:287-504 (host, single thread, pixel order and mask side effects as in the reference, the sky
+// gate of its BUILD_NCNN branch included when `Sky segment` is set). Colour: the grey image replicated to three channels.
 size_t RunFusion(const ConfigParams& config, std::vector<Scene>& Scenes) {
     const size_t n = Scenes.size();
     std::vector<Camera> cams(n);
     std::vector<std::vector<float>> depths(n), normals(n);
-    std::vector<std::vector<unsigned char>> masks(n);
+    std::vector<std::vector<unsigned char>> masks(n), sky(n);
     std::vector<int> W(n, 0), H(n, 0);
     const std::string image_folder = config.input_folder + "/images", cam_folder = config.input_folder + "/cams";
     for (size_t i = 0; i < n; ++i) {
@@ -78,6 +77,7 @@ size_t RunFusion(const ConfigParams& config, std::vector<Scene>& Scenes) {
             throw std::runtime_error("fusion: missing results in " + folder);
         W[i] = w; H[i] = h;
         masks[i].assign((size_t)w * h, 0);
+        if (config.sky_seg) sky[i] = readSkyMask(folder, w, h);                    // :358-373
         if (Scenes[i].image.empty() && !readGrayImage(image_folder, id, Scenes[i].image)) throw std::runtime_error("fusion: missing image " + id8(id));
         const GrayImage& im = Scenes[i].image;      // RescaleImageAndCamera, :264-285
         if (im.width != w || im.height != h) {
@@ -102,6 +102,7 @@ size_t RunFusion(const ConfigParams& config, std::vector<Scene>& Scenes) {
             for (int c = 0; c < cols; ++c) {
                 const size_t idx = (size_t)r * cols + c;
                 if (masks[i][idx] == 1) continue;
+                if (!sky[i].empty() && sky[i][idx] > 0) { masks[i][idx] = 1; continue; }   // :385-388
                 const float ref_depth = depths[i][idx];
                 if (ref_depth <= 0.0f) continue;
                 const float* rn = &normals[i][3 * idx];
@@ -194,6 +195,10 @@ size_t RunFusionGPU(const ConfigParams& config, std::vector<Scene>& Scenes) {
         std::vector<unsigned char> gray(im.px.size());
         for (size_t k = 0; k < gray.size(); ++k) gray[k] = (unsigned char)std::min(255.f, std::max(0.f, std::round(im.px[k])));
         check(mpmvs_fusion_set_view(f, i, &cam, depth.data(), normal.data(), gray.data()), "mpmvs_fusion_set_view");
+        if (config.sky_seg) {
+            const std::vector<unsigned char> sky = readSkyMask(folder, w, h);
+            if (!sky.empty()) check(mpmvs_fusion_set_sky_mask(f, i, sky.data()), "mpmvs_fusion_set_sky_mask");
+        }
         for (size_t j = 0; j < Scenes[i].srcID.size(); ++j) {
             const int s = Scenes[i].srcID[j];
             lists[(size_t)i * max_list + j] = (s >= 0 && s < n && Scenes[s].estimate) ? s : -1;
@@ -247,6 +252,10 @@ int main(int argc, char* argv[]) {
         }
         const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
         printf("cost time is %.10f us\n", us);
+        if (config.sky_seg) {                               // main.cpp:44-46
+            const int n_sky = GenerateSkyRegionMask(Scenes, config);
+            std::cout << "refined " << n_sky << " sky masks" << std::endl;
+        }
         if (fusion) {
             const auto f0 = std::chrono::steady_clock::now();
             const size_t npts = gpu_fusion ? RunFusionGPU(config, Scenes) : RunFusion(config, Scenes);

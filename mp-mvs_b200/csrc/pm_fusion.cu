@@ -28,6 +28,7 @@ struct FusionView {
     const unsigned char* gray;   // [H][W]
     unsigned char* mask_prev;    // masks as of the start of the current image's launch
     unsigned char* mask_next;    // masks set during the current launch
+    const unsigned char* sky;    // optional [H][W], > 0 = sky (skymask_refine, cpp:358-373)
     int W, H;
 };
 
@@ -115,6 +116,12 @@ __global__ void __launch_bounds__(256) pm_mask_merge_kernel(unsigned char* prev,
     if (i < n && next[i]) prev[i] = 1;
 }
 
+// cpp:385-388: when an image's turn comes, its sky pixels are masked and skipped (earlier images could still use them as evidence)
+__global__ void __launch_bounds__(256) pm_mask_sky_kernel(unsigned char* prev, unsigned char* next, const unsigned char* sky, size_t n) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n && sky[i] > 0) { prev[i] = 1; next[i] = 1; }
+}
+
 }  // namespace
 
 struct mpmvs_fusion {
@@ -177,6 +184,18 @@ int mpmvs_fusion_set_view(mpmvs_fusion* f, int index, const mpmvs_camera* cam, c
     return MPMVS_OK;
 }
 
+int mpmvs_fusion_set_sky_mask(mpmvs_fusion* f, int index, const uint8_t* sky) {
+    if (!f || index < 0 || index >= f->n || !sky) return MPMVS_E_ARG;
+    FusionView& v = f->hviews[index];
+    if (!v.W) return MPMVS_E_ARG;    // mpmvs_fusion_set_view first
+    FCK(cudaSetDevice(f->device));
+    const size_t wh = (size_t)v.W * v.H;
+    unsigned char* d = const_cast<unsigned char*>(v.sky);
+    if (!d) { FCK(cudaMalloc((void**)&d, wh)); f->owned.push_back(d); v.sky = d; }
+    FCK(cudaMemcpy(d, sky, wh, cudaMemcpyHostToDevice));
+    return MPMVS_OK;
+}
+
 // src_lists: n_images rows of `max_list` view indices; row i = [i, its sources...] padded with -2 (end); -1 = a listed
 // source that was not estimated. use_dynamic_consistency: "Use dynamic_consistency to fuse" (cpp:451 vs 474).
 int mpmvs_fusion_run(mpmvs_fusion* f, const int* src_lists, int max_list, int use_dynamic_consistency, uint64_t* n_points, float* ms) {
@@ -225,6 +244,7 @@ int mpmvs_fusion_run(mpmvs_fusion* f, const int* src_lists, int max_list, int us
         int num_ngb = 0;
         while (num_ngb < max_list && row[num_ngb] != -2) ++num_ngb;
         const size_t wh = (size_t)v.W * v.H;
+        if (v.sky) pm_mask_sky_kernel<<<(unsigned)((wh + 255) / 256), 256>>>(v.mask_prev, v.mask_next, v.sky, wh);
         pm_fuse_kernel<<<dim3((v.W + 31) / 32, (v.H + 7) / 8), dim3(32, 8)>>>(f->dviews, i, d_src + (size_t)i * max_list, num_ngb,
                                                                              use_dynamic_consistency ? 1 : 0, tmp, keep);
         cub::DeviceSelect::Flagged(d_cub, cub_bytes, tmp, keep, f->d_points + f->n_points, d_num, (int)wh);

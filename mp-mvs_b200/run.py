@@ -5,8 +5,8 @@
 
 Reads the same config.yaml keys, `images/%08d.jpg` (or the decoded `.pgm` sidecar), `cams/%08d_cam.txt` and `pair.txt`, runs
 stage 1 and the geometric-consistency iterations sharded by reference image (pipeline.DensePipeline) and writes
-`<Output-folder>/MPMVS/2333_%08d/{depths,normals,costs}.dmb` with background writer threads. Fusion stays with the C++ host
-(mp-mvs_b200/mpmvs_main --fusion-only is not needed: the files are the reference's).
+`<Output-folder>/MPMVS/2333_%08d/{depths,normals,costs}.dmb` with background writer threads, then (optionally) refines the sky
+masks (`Sky segment: 1`) and fuses the depth maps on rank 0's GPU into `MPMVS_model.ply`.
 """
 from __future__ import annotations
 
@@ -41,6 +41,60 @@ def load_image(folder: str, image_id: int, max_size: int):
     nw, nh = int(round(float(np.float32(w) * factor))), int(round(float(np.float32(h) * factor)))
     out = cv2.resize(img.astype(np.float32), (nw, nh), interpolation=cv2.INTER_LINEAR)
     return out, nw / np.float32(w), nh / np.float32(h)
+
+
+def sky_image_size(w: int, h: int, max_size: int):
+    """Size rule of GenerateSkyRegionMask (PatchMatch.cpp:21-33): the image size PatchMatch worked at."""
+    if w <= max_size and h <= max_size:
+        return w, h
+    factor = min(np.float32(max_size) / np.float32(w), np.float32(max_size) / np.float32(h))
+    return int(round(float(np.float32(w) * factor))), int(round(float(np.float32(h) * factor)))
+
+
+def generate_sky_masks(cfg: dict, refs, rank: int, world: int, device: int):
+    """GenerateSkyRegionMask (PatchMatch.cpp:4-57) without the network: `<out>/MPMVS/2333_%08d/skymask.jpg` (255 x the sky
+    probability of any segmenter, any size; the reference's own ncnn model writes exactly this file, cpp:42-44) is refined by
+    joint-bilateral upsampling on the GPU (mpmvs_sky_mask_refine) into skymask_refine.jpg, which gates fusion, plus the
+    skymask_fuse.jpg preview (image_mask_fuse, SkyRegionDetect.cpp:462-478). Images are sharded over the ranks.
+    Returns the number of masks this rank refined."""
+    import cv2
+
+    from mpmvs_b200 import capi
+
+    inp, out = cfg["Input-folder"].rstrip("/"), cfg["Output-folder"].rstrip("/")
+    done = 0
+    for k, i in enumerate(refs):
+        if k % world != rank:
+            continue
+        folder = io_formats.result_dir(out, i)
+        coarse = cv2.imread(os.path.join(folder, "skymask.jpg"), cv2.IMREAD_GRAYSCALE)
+        if coarse is None:
+            continue
+        bgr = cv2.imread(os.path.join(inp, "images", f"{i:08d}.jpg"), cv2.IMREAD_COLOR)
+        if bgr is None:
+            raise FileNotFoundError(f"Can not read this image ! {i:08d}")
+        w, h = sky_image_size(bgr.shape[1], bgr.shape[0], int(cfg["Max image size"]))
+        if (w, h) != (bgr.shape[1], bgr.shape[0]):
+            bgr = cv2.resize(bgr, (w, h), interpolation=cv2.INTER_LINEAR)          # cpp:36
+        refined, _, _ = capi.sky_mask_refine(bgr, coarse.astype(np.float32) / np.float32(255), device=device)
+        cv2.imwrite(os.path.join(folder, "skymask_refine.jpg"), refined)           # cpp:47-50
+        fuse = bgr.copy()
+        fuse[refined > 0] = 0
+        cv2.imwrite(os.path.join(folder, "skymask_fuse.jpg"), fuse)
+        done += 1
+    return done
+
+
+def load_sky_mask(out: str, image_id: int, shape):
+    """The sky gate RunFusion reads (PatchMatch.cpp:358-373): skymask_refine.jpg, brought to the depth map's size."""
+    import cv2
+
+    m = cv2.imread(os.path.join(io_formats.result_dir(out, image_id), "skymask_refine.jpg"), cv2.IMREAD_GRAYSCALE)
+    if m is None:
+        return None
+    if m.shape != tuple(shape):
+        m = cv2.resize(m, (shape[1], shape[0]), interpolation=cv2.INTER_LINEAR)
+    return m
 
 
 def load_scene(cfg: dict, rank: int, world: int):
@@ -103,6 +157,10 @@ def main():
     out = cfg["Output-folder"].rstrip("/")
     p.write_results(out)
     t3 = time.time()
+    sky_seg = bool(int(cfg["Sky segment"]))
+    if sky_seg:                                            # main.cpp:44-46
+        n_sky = generate_sky_masks(cfg, sorted(e.ref_id for e in entries if e.estimate), rank, world, local)
+        print(f"rank {rank}: refined {n_sky} sky masks in {time.time() - t3:.2f} s")
     if dist is not None:
         dist.barrier()
     t4 = t3
@@ -120,6 +178,9 @@ def main():
             cam = cams[i]
             cam.height, cam.width = d.shape
             fz.set_view(i, io_formats.pack_cameras([cam]), d, nrm, np.clip(np.rint(img), 0, 255).astype(np.uint8))
+            sky = load_sky_mask(out, i, d.shape) if sky_seg else None
+            if sky is not None:
+                fz.set_sky_mask(i, sky)
             lists[i] = [i] + [j if j in by_ref else -1 for j in by_ref[i].src_ids[1:]]
         pts, fus_ms = fz.run(lists, bool(int(cfg["Use dynamic_consistency to fuse"])))
         fz.destroy()

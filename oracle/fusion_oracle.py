@@ -35,8 +35,9 @@ def _project(X, cam):
     return u.astype(np.float32), v.astype(np.float32), depth.astype(np.float32)
 
 
-def fuse(cams, depths, normals, grays, src_lists, dynamic=True):
+def fuse(cams, depths, normals, grays, src_lists, dynamic=True, sky=None):
     """cams: packed camera records; depths/normals/grays: per image arrays; src_lists[i] = [i, sources...] or None.
+    sky: optional per-image uint8 masks (> 0 = sky, None = no mask): masked when the image's turn comes (cpp:385-388).
     Returns (n, 9) float32 points in the kernel's order (images in order, raster order inside an image)."""
     n = len(cams)
     masks = [np.zeros(d.shape, bool) for d in depths]
@@ -47,6 +48,8 @@ def fuse(cams, depths, normals, grays, src_lists, dynamic=True):
         h, w = depths[i].shape
         ys, xs = np.mgrid[0:h, 0:w].astype(np.float32)
         ref_depth = depths[i].astype(np.float32)
+        if sky is not None and sky[i] is not None:
+            masks[i] |= np.asarray(sky[i]) > 0
         alive = (~masks[i]) & (ref_depth > 0)
         PX = _world(xs, ys, ref_depth, cams[i])
         rn = normals[i].astype(np.float32)

@@ -32,17 +32,30 @@ struct Vec {
 };
 typedef Vec<float, 3> Vec3f;
 typedef Vec<uchar, 3> Vec3b;
+struct Size {
+    int width, height;
+    Size() : width(0), height(0) {}
+    Size(int w, int h) : width(w), height(h) {}
+};
+enum { INTER_LINEAR = 1 };
+#ifndef CV_32F
+#define CV_32F 5
+#endif
 // A non-owning view of a float image; enough for the harness to hand raw rows to cudaMemcpy2DToArray.
 struct Mat {
     int rows, cols;
     void* data;
     size_t step[2];
     Mat() : rows(0), cols(0), data(nullptr) { step[0] = step[1] = 0; }
+    Mat(Size s, int) : rows(s.height), cols(s.width), data(nullptr) { step[0] = step[1] = 0; }
+    Mat clone() const { return *this; }
     bool empty() const { return data == nullptr; }
     template <typename T> T* ptr(int r = 0) { return (T*)((char*)data + r * step[0]); }
     template <typename T> const T* ptr(int r = 0) const { return (const T*)((const char*)data + r * step[0]); }
 };
 template <typename T>
 struct Mat_ : public Mat {};
+// host helper of SkySegment/src/SkyRegionDetect.cu:37-66 only needs this to exist; the harness never calls that helper
+inline void resize(const Mat&, Mat&, Size, double = 0, double = 0, int = INTER_LINEAR) {}
 }  // namespace cv
 #endif

@@ -28,7 +28,7 @@ VARIANTS = {
 
 def build(name):
     out = os.path.join(OUT, f"libmpmvs_b200_{name}.so")
-    cmd = ["/usr/local/cuda/bin/nvcc"] + BASE + VARIANTS[name] + ["-o", out, os.path.join(CSRC, "pm_kernels.cu"), os.path.join(CSRC, "pm_prior.cu"), os.path.join(CSRC, "pm_fusion.cu"), os.path.join(CSRC, "pm_capi.cu")]
+    cmd = ["/usr/local/cuda/bin/nvcc"] + BASE + VARIANTS[name] + ["-o", out, os.path.join(CSRC, "pm_kernels.cu"), os.path.join(CSRC, "pm_prior.cu"), os.path.join(CSRC, "pm_fusion.cu"), os.path.join(CSRC, "pm_sky.cu"), os.path.join(CSRC, "pm_capi.cu")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     return name, r.returncode, r.stderr[-400:]
 
