@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 import pkgload  # noqa: E402
 
 pkgload.load_package()
-from mpmvs_b200 import io_formats, pipeline  # noqa: E402
+from mpmvs_b200 import io_formats, pipeline, previews  # noqa: E402
 
 
 def load_image(folder: str, image_id: int, max_size: int):
@@ -156,6 +156,13 @@ def main():
     t2 = time.time()
     out = cfg["Output-folder"].rstrip("/")
     p.write_results(out)
+    for ref in p.my_refs:                                  # costs.jpg next to the .dmb files (PatchMatch.cpp:624-629)
+        folder = io_formats.result_dir(out, ref)
+        previews.save_cost(io_formats.read_dmb(os.path.join(folder, "costs.dmb")), os.path.join(folder, "costs.jpg"))
+    if any(int(cfg[k]) for k in ("Save Dmb as JPG", "Save Prior Dmb as JPG", "Save Cost Map", "Save Normal Map")):   # main.cpp:51-53
+        print("Start save data as jpg")
+        previews.save_dmb_as_jpg(cfg, p.my_refs)
+        print("save data success")
     t3 = time.time()
     sky_seg = bool(int(cfg["Sky segment"]))
     if sky_seg:                                            # main.cpp:44-46

@@ -196,12 +196,15 @@ def test_cli_sky_segment(tmp_path):
     from mpmvs_b200 import capi, io_formats
 
     sc, root, yaml = write_scene(tmp_path, **{"Geometric consistency iterations": 0, "Planer prior": 0,
-                                              "Geometric consistency planer prior": 0, "Sky segment": 1})
+                                              "Geometric consistency planer prior": 0, "Sky segment": 1,
+                                              "Save Dmb as JPG": 1, "Save Normal Map": 1})
     place_coarse_masks(sc, root)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "mp-mvs_b200", "run.py"), yaml, "--seed", "3"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
     assert f"refined {sc.num_views} sky masks" in r.stdout
     n_cli = int(r.stdout.split("fusion: ")[1].split(" points")[0])
+    for name in ("costs.jpg", "depths.jpg", "normals.jpg"):          # previews (PatchMatch.cpp:624-629, main.cpp:51-53)
+        assert os.path.getsize(os.path.join(root, "MPMVS", "2333_00000004", name)) > 500, name
     cams = io_formats.pack_cameras(sc.cams)
     counts = {}
     for gate in (False, True):
