@@ -20,6 +20,7 @@
 #include <iomanip>
 #include <iostream>
 #include <map>
+#include <memory>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -49,7 +50,9 @@ struct Scene {                                     // utility.h:17-26
     std::vector<int> srcID;
     GrayImage image;                                // decoded (and, above max_image_size, resized) grey image, cached
     int orig_width = 0, orig_height = 0;            // size of the file on disk (K is scaled by image size / this)
-    std::vector<float> depth, normal, cost;         // latest results of this image (what its .dmb files hold), kept in memory
+    // latest results of this image (what its .dmb files hold), kept in memory; shared so that the background .dmb writer
+    // and a later pass can hold the same buffers
+    std::shared_ptr<const std::vector<float>> depth, normal, cost;
     int max_image_size = 3200;
 };
 struct ConfigParams {                              // utility.h:28-46
@@ -76,6 +79,13 @@ bool readGrayFile(const std::string& path_without_ext, GrayImage& out);        /
 bool readColorFile(const std::string& path_without_ext, int& w, int& h, std::vector<unsigned char>& bgr);   // .ppm or .jpg, B G R interleaved
 bool writePgm(const std::string& path, int w, int h, const unsigned char* px);
 GrayImage resizeLinear(const GrayImage& src, int new_cols, int new_rows);       // cv::resize(..., INTER_LINEAR) on float
+// Background .dmb writers: ProcessProblem hands its three result maps over and returns; Flush() waits for the files
+// (the reference writes them synchronously, PatchMatch.cpp:620-633).
+void SubmitDmb(const std::string& path, int h, int w, int nb, std::shared_ptr<const std::vector<float>> data);
+void FlushDmbWriters();
+// seconds spent per host phase of ProcessProblem since the start of the process (printed by mpmvs_main --profile)
+struct HostPhaseTimes { double init = 0, upload = 0, run = 0, prior = 0, collect = 0, write = 0; };
+HostPhaseTimes& PhaseTimes();
 int GenerateSkyRegionMask(std::vector<Scene>& Scenes, const ConfigParams& config);   // PatchMatch.cpp:4-57 minus the network
 std::vector<unsigned char> readSkyMask(const std::string& result_folder, int w, int h);   // PatchMatch.cpp:358-373
 
@@ -142,7 +152,7 @@ class PatchMatchCUDA {
     int tex_format_ = MPMVS_TEX_F32;
     mpmvs_problem* h_ = nullptr;
     std::vector<const GrayImage*> images_;         // the decoded images cached in Scenes (not copied per call)
-    std::vector<std::vector<float>> depths_;
+    std::vector<std::shared_ptr<const std::vector<float>>> depths_;   // the sources' depth maps of the previous pass (not copied)
     std::vector<Camera> cameras_;
     std::vector<float4> planes_;
     std::vector<float> costs_, geom_costs_;

@@ -6,7 +6,12 @@
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
+#include <mutex>
+#include <thread>
 
 #ifdef MPMVS_WITH_NVJPEG
 #include <cuda_runtime.h>
@@ -133,6 +138,60 @@ bool writeDmb(const std::string& path, int h, int w, int nb, const float* data) 
     return true;
 }
 
+// ---------------------------------------------------------------------------------------------- background writers
+namespace {
+struct DmbJob { std::string path; int h, w, nb; std::shared_ptr<const std::vector<float>> data; };
+class DmbWriterPool {
+  public:
+    explicit DmbWriterPool(int n) { for (int i = 0; i < n; ++i) threads_.emplace_back([this] { loop(); }); }
+    ~DmbWriterPool() {
+        { std::lock_guard<std::mutex> l(m_); stop_ = true; }
+        cv_.notify_all();
+        for (std::thread& t : threads_) t.join();
+    }
+    void submit(DmbJob j) {
+        { std::lock_guard<std::mutex> l(m_); q_.push_back(std::move(j)); ++pending_; }
+        cv_.notify_one();
+    }
+    void flush() {
+        std::unique_lock<std::mutex> l(m_);
+        done_.wait(l, [this] { return pending_ == 0; });
+        if (failed_) { failed_ = false; throw std::runtime_error("writing a .dmb file failed"); }
+    }
+  private:
+    void loop() {
+        for (;;) {
+            DmbJob j;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [this] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                j = std::move(q_.front());
+                q_.pop_front();
+            }
+            const bool ok = writeDmb(j.path, j.h, j.w, j.nb, j.data->data());
+            std::lock_guard<std::mutex> l(m_);
+            if (!ok) failed_ = true;
+            if (--pending_ == 0) done_.notify_all();
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::deque<DmbJob> q_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    int pending_ = 0;
+    bool stop_ = false, failed_ = false;
+};
+DmbWriterPool& writers() { static DmbWriterPool pool(4); return pool; }
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+}  // namespace
+
+void SubmitDmb(const std::string& path, int h, int w, int nb, std::shared_ptr<const std::vector<float>> data) {
+    writers().submit(DmbJob{path, h, w, nb, std::move(data)});
+}
+void FlushDmbWriters() { writers().flush(); }
+HostPhaseTimes& PhaseTimes() { static HostPhaseTimes t; return t; }
+
 // ---------------------------------------------------------------------------------------------- images
 static bool readPgm(const std::string& path, GrayImage& out) {
     std::ifstream f(path, std::ios::binary);
@@ -159,6 +218,8 @@ static bool readJpegLuma(const std::string& path, GrayImage& out) {
     std::vector<unsigned char> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
     static nvjpegHandle_t handle = nullptr;
     static nvjpegJpegState_t state = nullptr;
+    static std::mutex decoder_mutex;               // one decoder state: callers on several threads take turns
+    std::lock_guard<std::mutex> lock(decoder_mutex);
     if (!handle) {
         if (nvjpegCreateSimple(&handle) != NVJPEG_STATUS_SUCCESS) return false;
         if (nvjpegJpegStateCreate(handle, &state) != NVJPEG_STATUS_SUCCESS) return false;
@@ -369,10 +430,10 @@ void PatchMatchCUDA::PatchMatchInit(std::vector<Scene>& Scenes, int ID) {
         for (size_t i = 1; i < srcID.size(); ++i) {
             const size_t wh = (size_t)cameras_[i].width * cameras_[i].height;
             const Scene& src = Scenes[srcID[i]];
-            if (src.depth.size() == wh) { depths_.push_back(src.depth); continue; }   // this process wrote that file itself
+            if (src.depth && src.depth->size() == wh) { depths_.push_back(src.depth); continue; }   // this process wrote that file itself
             int h, w, nb;
-            std::vector<float> d;
-            if (!readDmb(input_folder_ + "/MPMVS/2333_" + id8(srcID[i]) + "/depths.dmb", h, w, nb, d)) d.assign(wh, 0.f);
+            auto d = std::make_shared<std::vector<float>>();
+            if (!readDmb(input_folder_ + "/MPMVS/2333_" + id8(srcID[i]) + "/depths.dmb", h, w, nb, *d)) d->assign(wh, 0.f);
             depths_.push_back(std::move(d));
         }
     }
@@ -394,20 +455,23 @@ void PatchMatchCUDA::CudaMemInit(Scene& scene) {
     planes_.resize(wh); costs_.resize(wh); geom_costs_.assign(wh, 0.f);
     if (geom_) {
         std::vector<const float*> dep(depths_.size());
-        for (size_t i = 0; i < depths_.size(); ++i) dep[i] = depths_[i].data();
+        for (size_t i = 0; i < depths_.size(); ++i) dep[i] = depths_[i]->data();
         check(mpmvs_set_src_depths(h_, dep.data()), "mpmvs_set_src_depths");
         // own result of the previous pass (PatchMatch.cpp:1051-1087)
         const std::string folder = input_folder_ + "/MPMVS/2333_" + id8(ref_id_);
         int h, w, nb;
-        std::vector<float> d, n, c;
-        if (scene.depth.size() == wh && scene.normal.size() == 3 * wh && scene.cost.size() == wh) {
-            d = scene.depth; n = scene.normal; c = scene.cost;      // written by this process in the previous pass
-        } else if (!readDmb(folder + "/depths.dmb", h, w, nb, d) || !readDmb(folder + "/normals.dmb", h, w, nb, n) ||
-                   !readDmb(folder + "/costs.dmb", h, w, nb, c) || d.size() != wh) {
+        std::vector<float> fd, fn, fc;
+        const float *d, *n, *c;
+        if (scene.depth && scene.normal && scene.cost && scene.depth->size() == wh && scene.normal->size() == 3 * wh && scene.cost->size() == wh) {
+            d = scene.depth->data(); n = scene.normal->data(); c = scene.cost->data();      // written by this process in the previous pass
+        } else if (!readDmb(folder + "/depths.dmb", h, w, nb, fd) || !readDmb(folder + "/normals.dmb", h, w, nb, fn) ||
+                   !readDmb(folder + "/costs.dmb", h, w, nb, fc) || fd.size() != wh) {
             throw std::runtime_error("geometric consistency pass needs the previous results in " + folder);
+        } else {
+            d = fd.data(); n = fn.data(); c = fc.data();
         }
-        for (size_t i = 0; i < wh; ++i) { planes_[i] = {n[3 * i], n[3 * i + 1], n[3 * i + 2], d[i]}; costs_[i] = c[i]; }
-        check(mpmvs_set_state(h_, (const float*)planes_.data(), costs_.data()), "mpmvs_set_state");
+        for (size_t i = 0; i < wh; ++i) planes_[i] = {n[3 * i], n[3 * i + 1], n[3 * i + 2], d[i]};
+        check(mpmvs_set_state(h_, (const float*)planes_.data(), c), "mpmvs_set_state");
     }
 }
 
@@ -478,14 +542,19 @@ void ProcessProblem(const std::string& input_folder, const std::string& output_f
     const std::string result_folder = output_folder + "/2333_" + id8(scene.refID);
     mkdir(result_folder.c_str(), 0777);
 
+    HostPhaseTimes& T = PhaseTimes();
+    double t0 = now_s();
     PatchMatchCUDA MP(0);
     MP.SetFolder(input_folder, output_folder);
     MP.SetTexFormat(tex_format);
     MP.SetGeomConsistencyParams(geom_consistency, planar_prior);
     MP.PatchMatchInit(Scenes, ID);
+    T.init += now_s() - t0; t0 = now_s();
     MP.AllocatePatchMatch();
     MP.CudaMemInit(Scenes[ID]);
+    T.upload += now_s() - t0; t0 = now_s();
     MP.Run(seed);
+    T.run += now_s() - t0; t0 = now_s();
     if (planar_prior) {
         std::cout << "Run Planar Prior PatchMatch MVS ..." << std::endl;
         MP.SetPlanarPriorParams();
@@ -494,20 +563,26 @@ void ProcessProblem(const std::string& input_folder, const std::string& output_f
         MP.BuildPlanarPrior(&st);       // vertices, Delaunay, rasterisation, plane fit, range check, upload (cpp:536-600)
         MP.Run(seed ^ 0x5DEECE66DULL);
         MP.SetGeomConsistencyParams(geom_consistency, planar_prior);
+        T.prior += now_s() - t0; t0 = now_s();
     }
     const int width = MP.GetReferenceImageWidth(), height = MP.GetReferenceImageHeight();
-    std::vector<float> depths((size_t)width * height), normals((size_t)width * height * 3);
-    for (size_t i = 0; i < depths.size(); ++i) {
-        const float4 pl = MP.GetPlaneHypothesis((int)i);
-        depths[i] = pl.w;
-        normals[3 * i] = pl.x; normals[3 * i + 1] = pl.y; normals[3 * i + 2] = pl.z;
+    auto depths = std::make_shared<std::vector<float>>((size_t)width * height);
+    auto normals = std::make_shared<std::vector<float>>((size_t)width * height * 3);
+    const float4* pl = MP.planes().data();
+    float *dd = depths->data(), *nn = normals->data();
+    for (size_t i = 0; i < depths->size(); ++i) {
+        dd[i] = pl[i].w;
+        nn[3 * i] = pl[i].x; nn[3 * i + 1] = pl[i].y; nn[3 * i + 2] = pl[i].z;
     }
-    writeDmb(result_folder + "/depths.dmb", height, width, 1, depths.data());
-    writeDmb(result_folder + "/normals.dmb", height, width, 3, normals.data());
-    writeDmb(result_folder + "/costs.dmb", height, width, 1, MP.costs().data());
-    scene.depth = std::move(depths);            // later passes (and other images of this pass: the reference's in-place,
-    scene.normal = std::move(normals);          // Gauss-Seidel order) read these instead of the files
-    scene.cost = MP.costs();
+    auto costs = std::make_shared<std::vector<float>>(MP.costs());
+    T.collect += now_s() - t0; t0 = now_s();
+    // the three result files (PatchMatch.cpp:620-633) are written in the background; later passes (and other images of
+    // this pass: the reference's in-place, Gauss-Seidel order) read the buffers, not the files
+    SubmitDmb(result_folder + "/depths.dmb", height, width, 1, depths);
+    SubmitDmb(result_folder + "/normals.dmb", height, width, 3, normals);
+    SubmitDmb(result_folder + "/costs.dmb", height, width, 1, costs);
+    scene.depth = depths; scene.normal = normals; scene.cost = costs;
+    T.write += now_s() - t0;
     std::cout << "Processing image " << id8(scene.refID) << " done!" << std::endl;
     MP.Release(Scenes, ID);
 }

@@ -2,16 +2,26 @@
 // config.yaml -> pair.txt -> stage 1 (multi-scale photometric [+ planar prior]) -> geometric-consistency iterations
 // [+ planar prior] -> fusion -> MPMVS_model.ply, on the same dense-folder layout and with the same output files.
 //
-//   mpmvs_main [config.yaml] [--seed N] [--tex f32|u8] [--no-fusion] [--gpu-fusion]
+//   mpmvs_main [config.yaml] [--seed N] [--tex f32|u8] [--no-fusion] [--gpu-fusion] [--resident [--in-flight N] [--device D]] [--profile]
+//
+// Default: the reference's strictly sequential order (one ProcessProblem at a time, results exchanged in place).
+// --resident: every view uploaded once into a per-GPU image cache, one resident handle per reference image, depth maps
+// exchanged between passes in device memory (Jacobi order: every image reads the previous pass), N images in flight on
+// host threads -- the single-GPU form of mp-mvs_b200/pipeline.py, in C++.
 //
 // The reference bakes the config path in at cmake time (include/ProjectPath.h.in) and takes no arguments.
 #include <sys/stat.h>
 
+#include <cuda_runtime.h>
+
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <thread>
 
 #include "PatchMatchCUDA.h"
 
@@ -75,6 +85,7 @@ size_t RunFusion(const ConfigParams& config, std::vector<Scene>& Scenes) {
         int h, w, nb;
         if (!readDmb(folder + "/depths.dmb", h, w, nb, depths[i]) || !readDmb(folder + "/normals.dmb", h, w, nb, normals[i]))
             throw std::runtime_error("fusion: missing results in " + folder);
+        Scenes[i].depth.reset(); Scenes[i].normal.reset(); Scenes[i].cost.reset();     // the files are the interface from here on
         W[i] = w; H[i] = h;
         masks[i].assign((size_t)w * h, 0);
         if (config.sky_seg) sky[i] = readSkyMask(folder, w, h);                    // :358-373
@@ -182,19 +193,34 @@ size_t RunFusionGPU(const ConfigParams& config, std::vector<Scene>& Scenes) {
         const int id = Scenes[i].refID;
         Camera cam = ReadCamera(cam_folder + "/" + id8(id) + "_cam.txt");
         const std::string folder = config.input_folder + "/MPMVS/2333_" + id8(id);
-        int h, w, nb;
-        std::vector<float> depth, normal;
-        if (!readDmb(folder + "/depths.dmb", h, w, nb, depth) || !readDmb(folder + "/normals.dmb", h, w, nb, normal))
-            throw std::runtime_error("fusion: missing results in " + folder);
+        int h = 0, w = 0, nb;
+        std::vector<float> fdepth, fnormal;
+        const float *depth_px, *normal_px;
+        const Scene& S = Scenes[i];
+        if (S.depth && S.normal && !S.image.empty() && S.depth->size() == (size_t)S.image.width * S.image.height &&
+            S.normal->size() == 3 * S.depth->size()) {          // this process produced the maps: no need to read its own files back
+            w = S.image.width; h = S.image.height;
+            depth_px = S.depth->data(); normal_px = S.normal->data();
+        } else {
+            if (!readDmb(folder + "/depths.dmb", h, w, nb, fdepth) || !readDmb(folder + "/normals.dmb", h, w, nb, fnormal))
+                throw std::runtime_error("fusion: missing results in " + folder);
+            depth_px = fdepth.data(); normal_px = fnormal.data();
+        }
         if (Scenes[i].image.empty() && !readGrayImage(image_folder, id, Scenes[i].image)) throw std::runtime_error("fusion: missing image " + id8(id));
-        GrayImage im = Scenes[i].image;
-        const int ow = Scenes[i].orig_width ? Scenes[i].orig_width : im.width, oh = Scenes[i].orig_height ? Scenes[i].orig_height : im.height;
-        if (im.width != w || im.height != h) im = resizeLinear(im, w, h);
+        const GrayImage* im = &Scenes[i].image;
+        GrayImage resized;
+        const int ow = Scenes[i].orig_width ? Scenes[i].orig_width : im->width, oh = Scenes[i].orig_height ? Scenes[i].orig_height : im->height;
+        if (im->width != w || im->height != h) { resized = resizeLinear(*im, w, h); im = &resized; }
         if (ow != w || oh != h) { cam.K[0] *= w / (float)ow; cam.K[2] *= w / (float)ow; cam.K[4] *= h / (float)oh; cam.K[5] *= h / (float)oh; }
         cam.width = w; cam.height = h;
-        std::vector<unsigned char> gray(im.px.size());
-        for (size_t k = 0; k < gray.size(); ++k) gray[k] = (unsigned char)std::min(255.f, std::max(0.f, std::round(im.px[k])));
-        check(mpmvs_fusion_set_view(f, i, &cam, depth.data(), normal.data(), gray.data()), "mpmvs_fusion_set_view");
+        std::vector<unsigned char> gray;
+        const unsigned char* gray_px = im->u8.data();
+        if (im->u8.size() != im->px.size()) {            // a resized image has no 8-bit original
+            gray.resize(im->px.size());
+            for (size_t k = 0; k < gray.size(); ++k) gray[k] = (unsigned char)std::min(255.f, std::max(0.f, std::round(im->px[k])));
+            gray_px = gray.data();
+        }
+        check(mpmvs_fusion_set_view(f, i, &cam, depth_px, normal_px, gray_px), "mpmvs_fusion_set_view");
         if (config.sky_seg) {
             const std::vector<unsigned char> sky = readSkyMask(folder, w, h);
             if (!sky.empty()) check(mpmvs_fusion_set_sky_mask(f, i, sky.data()), "mpmvs_fusion_set_sky_mask");
@@ -215,6 +241,181 @@ size_t RunFusionGPU(const ConfigParams& config, std::vector<Scene>& Scenes) {
     return cloud.size();
 }
 
+// ------------------------------------------------------------------------------------------------ resident pipeline
+static void cuda_ok(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+// The stage schedule of main() (main.cpp:19-41) with everything resident on one GPU. Returns the seconds spent in the
+// PatchMatch passes (set-up excluded, reported separately).
+static void RunResident(const ConfigParams& config, std::vector<Scene>& Scenes, uint64_t seed, int tex, int in_flight, int device) {
+    const int n = (int)Scenes.size();
+    const auto t_setup = std::chrono::steady_clock::now();
+    cuda_ok(cudaSetDevice(device), "cudaSetDevice");
+    const std::string image_folder = config.input_folder + "/images", cam_folder = config.input_folder + "/cams";
+    // 1. every view that some problem uses: decoded once (host threads), resized by PatchMatchInit's rule
+    std::vector<char> needed(n, 0);
+    for (const Scene& sc : Scenes)
+        if (sc.estimate) for (int id : sc.srcID) if (id >= 0 && id < n) needed[id] = 1;
+    std::vector<Camera> cams(n);
+    {
+        std::atomic<int> next{0};
+        std::atomic<bool> failed{false};
+        auto work = [&] {
+            for (int i; (i = next++) < n;) {
+                if (!needed[i]) continue;
+                Scene& sc = Scenes[i];
+                try {
+                    cams[i] = ReadCamera(cam_folder + "/" + id8(i) + "_cam.txt");
+                    if (sc.image.empty()) {
+                        if (!readGrayImage(image_folder, i, sc.image)) throw std::runtime_error("Can not read this image ! " + id8(i));
+                        sc.orig_width = sc.image.width; sc.orig_height = sc.image.height;
+                        const int m = config.MaxImageSize;        // PatchMatch.cpp:893-925
+                        if (sc.image.width > m || sc.image.height > m) {
+                            const float factor = std::min((float)m / sc.image.width, (float)m / sc.image.height);
+                            sc.image = resizeLinear(sc.image, (int)std::round(sc.image.width * factor), (int)std::round(sc.image.height * factor));
+                        }
+                    }
+                    const float sx = sc.image.width / (float)sc.orig_width, sy = sc.image.height / (float)sc.orig_height;
+                    if (sc.image.width != sc.orig_width || sc.image.height != sc.orig_height) {
+                        cams[i].K[0] *= sx; cams[i].K[2] *= sx; cams[i].K[4] *= sy; cams[i].K[5] *= sy;
+                    }
+                    cams[i].width = sc.image.width; cams[i].height = sc.image.height;
+                } catch (const std::exception& e) {
+                    std::cout << e.what() << std::endl;
+                    failed = true;
+                }
+            }
+        };
+        std::vector<std::thread> pool;
+        const int n_dec = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+        for (int t = 0; t < n_dec; ++t) pool.emplace_back(work);
+        for (std::thread& t : pool) t.join();
+        if (failed) throw std::runtime_error("resident pipeline: missing inputs");
+    }
+    int W = 0, H = 0;
+    bool all_u8 = tex == MPMVS_TEX_U8;
+    for (int i = 0; i < n; ++i) {
+        if (!needed[i]) continue;
+        const GrayImage& im = Scenes[i].image;
+        if (!W) { W = im.width; H = im.height; }
+        if (im.width != W || im.height != H) throw std::runtime_error("--resident needs equally sized views (one exchange buffer); use the default mode");
+        all_u8 = all_u8 && im.u8.size() == im.px.size();
+    }
+    if (!W) return;
+    // 2. the per-GPU image cache
+    mpmvs_image_cache* cache = nullptr;
+    check(mpmvs_cache_create_fmt(device, W, H, n, all_u8 ? MPMVS_TEX_U8 : MPMVS_TEX_F32, &cache), "mpmvs_cache_create_fmt");
+    for (int i = 0; i < n; ++i) {
+        if (!needed[i]) continue;
+        const GrayImage& im = Scenes[i].image;
+        check(all_u8 ? mpmvs_cache_put_u8(cache, i, im.u8.data(), W, H) : mpmvs_cache_put(cache, i, im.px.data(), W, H), "mpmvs_cache_put");
+    }
+    // 3. one resident handle per reference image
+    std::vector<mpmvs_problem*> handles(n, nullptr);
+    std::vector<int> refs;
+    for (int i = 0; i < n; ++i) {
+        if (!Scenes[i].estimate) continue;
+        refs.push_back(i);
+        check(mpmvs_create(device, nullptr, &handles[i]), "mpmvs_create");
+        std::vector<Camera> pc;
+        for (int id : Scenes[i].srcID) pc.push_back(cams[id]);
+        check(mpmvs_set_views_cached(handles[i], cache, (int)pc.size(), Scenes[i].srcID.data(), pc.data()), "mpmvs_set_views_cached");
+    }
+    // 4. depth maps of the previous pass, all images, in device memory (double-buffered: Jacobi)
+    const size_t wh = (size_t)W * H;
+    float* depth_buf[2] = {nullptr, nullptr};
+    if (config.geom_iterations > 0)
+        for (float*& b : depth_buf) { cuda_ok(cudaMalloc((void**)&b, wh * 4 * n), "cudaMalloc"); cuda_ok(cudaMemset(b, 0, wh * 4 * n), "cudaMemset"); }
+    printf("resident set-up (decode, upload, handles): %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_setup).count());
+
+    const auto t0 = std::chrono::steady_clock::now();
+    int cur = 0;
+    auto run_pass = [&](int stage, bool geom, bool planar) {
+        std::atomic<size_t> next{0};
+        std::atomic<bool> failed{false};
+        std::string err;
+        std::mutex err_m;
+        auto work = [&] {
+            for (size_t k; (k = next++) < refs.size();) {
+                const int i = refs[k];
+                mpmvs_problem* h = handles[i];
+                try {
+                    const uint64_t sd = seed + 1000003ULL * i + 7919ULL * stage;
+                    check(mpmvs_reset_params(h), "mpmvs_reset_params");                       // a fresh PatchMatchCUDA per call (cpp:516)
+                    check(mpmvs_set_geom_consistency_params(h, geom, planar), "mpmvs_set_geom_consistency_params");
+                    if (geom) {
+                        std::vector<const float*> dep;
+                        for (size_t j = 1; j < Scenes[i].srcID.size(); ++j) dep.push_back(depth_buf[cur] + wh * Scenes[i].srcID[j]);
+                        check(mpmvs_set_src_depths_device(h, dep.data(), nullptr), "mpmvs_set_src_depths_device");
+                    }
+                    check(mpmvs_run_async(h, sd), "mpmvs_run_async");
+                    if (planar) {
+                        check(mpmvs_set_planar_prior_params(h), "mpmvs_set_planar_prior_params");
+                        check(mpmvs_set_geom_consistency_params(h, 0, 1), "mpmvs_set_geom_consistency_params");
+                        check(mpmvs_build_prior(h, nullptr), "mpmvs_build_prior");           // blocks this thread only
+                        check(mpmvs_run_async(h, sd ^ 0x5DEECE66DULL), "mpmvs_run_async");
+                    }
+                    if (depth_buf[0]) check(mpmvs_export_depth_device(h, depth_buf[cur ^ 1] + wh * i, 0), "mpmvs_export_depth_device");
+                } catch (const std::exception& e) {
+                    std::lock_guard<std::mutex> l(err_m);
+                    err = e.what();
+                    failed = true;
+                }
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 0; t < std::max(1, in_flight); ++t) pool.emplace_back(work);
+        for (std::thread& t : pool) t.join();
+        for (int i : refs) check(mpmvs_synchronize(handles[i]), "mpmvs_synchronize");
+        if (failed) throw std::runtime_error(err);
+        cur ^= 1;
+    };
+    const auto stamp = [&](const char* what) {
+        printf("%s done after %.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    };
+    run_pass(0, false, !config.geomPlanarPrior && config.planar_prior);                       // main.cpp:19-26
+    stamp("stage 1");
+    for (int g = 0; g < config.geom_iterations; ++g) {                                         // main.cpp:28-41
+        run_pass(1 + g, true, config.geomPlanarPrior && g != config.geom_iterations - 1);
+        stamp("geometric consistency pass");
+    }
+    printf("cost time is %.10f us\n", std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
+    // 5. results: pinned staging, split into the three maps of a result folder, files written in the background
+    {
+        std::atomic<size_t> next{0};
+        std::atomic<bool> failed{false};
+        auto work = [&] {
+            float *pl = nullptr, *co = nullptr;
+            if (cudaSetDevice(device) != cudaSuccess || cudaMallocHost((void**)&pl, wh * 16) != cudaSuccess ||
+                cudaMallocHost((void**)&co, wh * 4) != cudaSuccess) { failed = true; cudaFreeHost(pl); return; }
+            for (size_t k; (k = next++) < refs.size();) {
+                const int i = refs[k];
+                if (mpmvs_get_results_async(handles[i], pl, co, nullptr) != MPMVS_OK || mpmvs_synchronize(handles[i]) != MPMVS_OK) { failed = true; break; }
+                auto depths = std::make_shared<std::vector<float>>(wh), normals = std::make_shared<std::vector<float>>(wh * 3);
+                auto costs = std::make_shared<std::vector<float>>(co, co + wh);
+                float *dd = depths->data(), *nn = normals->data();
+                for (size_t q = 0; q < wh; ++q) { nn[3 * q] = pl[4 * q]; nn[3 * q + 1] = pl[4 * q + 1]; nn[3 * q + 2] = pl[4 * q + 2]; dd[q] = pl[4 * q + 3]; }
+                const std::string folder = config.output_folder + "/2333_" + id8(Scenes[i].refID);
+                mkdir(folder.c_str(), 0777);
+                SubmitDmb(folder + "/depths.dmb", H, W, 1, depths);
+                SubmitDmb(folder + "/normals.dmb", H, W, 3, normals);
+                SubmitDmb(folder + "/costs.dmb", H, W, 1, costs);
+                Scenes[i].depth = depths; Scenes[i].normal = normals; Scenes[i].cost = costs;
+            }
+            cudaFreeHost(pl); cudaFreeHost(co);
+        };
+        std::vector<std::thread> pool;
+        for (int t = 0; t < 4; ++t) pool.emplace_back(work);
+        for (std::thread& t : pool) t.join();
+        if (failed) throw std::runtime_error("resident pipeline: reading the results back failed");
+    }
+    printf("results collected after %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    for (float* b : depth_buf) cudaFree(b);
+    for (mpmvs_problem* h : handles) if (h) mpmvs_destroy(h);
+    mpmvs_cache_destroy(cache);
+}
+
 }  // namespace mpmvs
 
 int main(int argc, char* argv[]) {
@@ -222,12 +423,17 @@ int main(int argc, char* argv[]) {
     std::string yaml = "config/config.yaml";
     uint64_t seed = 0x2333;
     int tex = MPMVS_TEX_F32;
-    bool fusion = true, gpu_fusion = false;
+    bool fusion = true, gpu_fusion = false, profile = false, resident = false;
+    int in_flight = 4, device = 0;
     for (int i = 1; i < argc; ++i) {
         if (!strcmp(argv[i], "--seed") && i + 1 < argc) seed = strtoull(argv[++i], nullptr, 0);
         else if (!strcmp(argv[i], "--tex") && i + 1 < argc) tex = !strcmp(argv[++i], "u8") ? MPMVS_TEX_U8 : MPMVS_TEX_F32;
         else if (!strcmp(argv[i], "--no-fusion")) fusion = false;
         else if (!strcmp(argv[i], "--gpu-fusion")) gpu_fusion = true;
+        else if (!strcmp(argv[i], "--profile")) profile = true;
+        else if (!strcmp(argv[i], "--resident")) resident = true;
+        else if (!strcmp(argv[i], "--in-flight") && i + 1 < argc) in_flight = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
         else yaml = argv[i];
     }
     try {
@@ -239,22 +445,34 @@ int main(int argc, char* argv[]) {
         const int num_img = (int)Scenes.size();
         std::cout << "There are " << num_img << " depthmaps need to be computed!\n" << std::endl;
         const auto t0 = std::chrono::steady_clock::now();
-        // stage 1: multi-scale-window PatchMatch (main.cpp:19-26)
-        bool planar_prior = !config.geomPlanarPrior && config.planar_prior;
-        for (int i = 0; i < num_img; ++i)
-            if (Scenes[i].estimate) ProcessProblem(config.input_folder, config.output_folder, Scenes, i, false, planar_prior, seed + 1000003ULL * i, tex);
-        // stage 2: geometric consistency [+ planar prior] (main.cpp:28-41)
-        for (int g = 0; g < config.geom_iterations; ++g) {
-            planar_prior = config.geomPlanarPrior && g != config.geom_iterations - 1;
+        if (resident) {
+            mkdir(config.output_folder.c_str(), 0777);
+            RunResident(config, Scenes, seed, tex, in_flight, device);
+        } else {
+            // stage 1: multi-scale-window PatchMatch (main.cpp:19-26)
+            bool planar_prior = !config.geomPlanarPrior && config.planar_prior;
             for (int i = 0; i < num_img; ++i)
-                if (Scenes[i].estimate)
-                    ProcessProblem(config.input_folder, config.output_folder, Scenes, i, true, planar_prior, seed + 1000003ULL * i + 7919ULL * (g + 1), tex);
+                if (Scenes[i].estimate) ProcessProblem(config.input_folder, config.output_folder, Scenes, i, false, planar_prior, seed + 1000003ULL * i, tex);
+            // stage 2: geometric consistency [+ planar prior] (main.cpp:28-41)
+            for (int g = 0; g < config.geom_iterations; ++g) {
+                planar_prior = config.geomPlanarPrior && g != config.geom_iterations - 1;
+                for (int i = 0; i < num_img; ++i)
+                    if (Scenes[i].estimate)
+                        ProcessProblem(config.input_folder, config.output_folder, Scenes, i, true, planar_prior, seed + 1000003ULL * i + 7919ULL * (g + 1), tex);
+            }
+            const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+            printf("cost time is %.10f us\n", us);
         }
-        const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
-        printf("cost time is %.10f us\n", us);
         if (config.sky_seg) {                               // main.cpp:44-46
             const int n_sky = GenerateSkyRegionMask(Scenes, config);
             std::cout << "refined " << n_sky << " sky masks" << std::endl;
+        }
+        FlushDmbWriters();
+        const double us_files = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+        printf("results on disk after %.10f us\n", us_files);
+        if (profile) {
+            const HostPhaseTimes& T = PhaseTimes();
+            printf("host phases (s): init %.3f upload %.3f run %.3f prior %.3f collect %.3f write %.3f\n", T.init, T.upload, T.run, T.prior, T.collect, T.write);
         }
         if (fusion) {
             const auto f0 = std::chrono::steady_clock::now();

@@ -85,6 +85,34 @@ def test_main_end_to_end(tmp_path, mode):
 
 
 @pytest.mark.gpu
+def test_main_resident_mode(tmp_path):
+    """--resident: image cache, one resident handle per image, depth maps exchanged in device memory (Jacobi), images in flight.
+    Same files, same quality as the sequential (reference-order) mode; bit-reproducible for any --in-flight."""
+    build_main()
+    sc, root, yaml = write_scene(tmp_path, **{"Geometric consistency iterations": 2, "Planer prior": 1,
+                                              "Geometric consistency planer prior": 1})
+    out = os.path.join(root, "MPMVS")
+
+    def run(*flags):
+        r = subprocess.run([MAIN, yaml, "--seed", "5", "--tex", "u8", "--gpu-fusion", *flags], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        d = [PKG.io_formats.read_dmb(os.path.join(out, f"2333_{i:08d}", "depths.dmb")) for i in range(sc.num_views)]
+        npts = int(r.stdout.split("store 3D points to ply file: ")[1].split(" points")[0])
+        return d, npts, r.stdout
+
+    d_seq, n_seq, _ = run()
+    d_a, n_a, log = run("--resident", "--in-flight", "3")
+    d_b, n_b, _ = run("--resident", "--in-flight", "1")
+    assert "resident set-up" in log and "cost time is" in log
+    for a, b in zip(d_a, d_b):
+        np.testing.assert_array_equal(a, b)                     # the order of the host threads does not matter
+    acc_seq = np.median([PKG.synth.accuracy_at(d, sc.gt_depth[i])[2] for i, d in enumerate(d_seq)])
+    acc_res = np.median([PKG.synth.accuracy_at(d, sc.gt_depth[i])[2] for i, d in enumerate(d_a)])
+    print("sequential / resident: accuracy", acc_seq, acc_res, "fused points", n_seq, n_a)
+    assert acc_res > 95 and abs(acc_res - acc_seq) < 0.5 and n_a == n_b and abs(n_a - n_seq) < 0.03 * n_seq
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("max_size", [3200, 200])
 def test_python_cli_matches_layout(tmp_path, max_size):
     """mp-mvs_b200/run.py: the sharded pipeline as a drop-in for main() over the same dense folder and YAML keys."""
