@@ -2,12 +2,13 @@
 // config.yaml -> pair.txt -> stage 1 (multi-scale photometric [+ planar prior]) -> geometric-consistency iterations
 // [+ planar prior] -> fusion -> MPMVS_model.ply, on the same dense-folder layout and with the same output files.
 //
-//   mpmvs_main [config.yaml] [--seed N] [--tex f32|u8] [--no-fusion] [--gpu-fusion] [--resident [--in-flight N] [--device D]] [--profile]
+//   mpmvs_main [config.yaml] [--seed N] [--tex f32|u8] [--no-fusion] [--gpu-fusion] [--resident [--in-flight N] [--device D] [--gpus G]] [--profile]
 //
 // Default: the reference's strictly sequential order (one ProcessProblem at a time, results exchanged in place).
 // --resident: every view uploaded once into a per-GPU image cache, one resident handle per reference image, depth maps
 // exchanged between passes in device memory (Jacobi order: every image reads the previous pass), N images in flight on
-// host threads -- the single-GPU form of mp-mvs_b200/pipeline.py, in C++.
+// host threads; with --gpus G the reference images are sharded over G GPUs and the depth maps all-gathered with peer copies
+// over NVLink -- mp-mvs_b200/pipeline.py's schedule in C++, one process driving all GPUs.
 //
 // The reference bakes the config path in at cmake time (include/ProjectPath.h.in) and takes no arguments.
 #include <sys/stat.h>
@@ -20,6 +21,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <thread>
 
@@ -246,12 +248,15 @@ static void cuda_ok(cudaError_t e, const char* what) {
     if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
 }
 
-// The stage schedule of main() (main.cpp:19-41) with everything resident on one GPU. Returns the seconds spent in the
-// PatchMatch passes (set-up excluded, reported separately).
-static void RunResident(const ConfigParams& config, std::vector<Scene>& Scenes, uint64_t seed, int tex, int in_flight, int device) {
+// The stage schedule of main() (main.cpp:19-41) with everything resident on the GPUs of `devices`: reference images in
+// contiguous blocks, one resident handle each, the depth maps of a pass all-gathered with peer-to-peer copies (one process
+// drives every GPU with host threads; pipeline.py is the one-process-per-GPU / NCCL form of the same schedule).
+// Results do not depend on the number of GPUs or of images in flight.
+static void RunResident(const ConfigParams& config, std::vector<Scene>& Scenes, uint64_t seed, int tex, int in_flight,
+                        const std::vector<int>& devices) {
     const int n = (int)Scenes.size();
     const auto t_setup = std::chrono::steady_clock::now();
-    cuda_ok(cudaSetDevice(device), "cudaSetDevice");
+    cuda_ok(cudaSetDevice(devices[0]), "cudaSetDevice");
     const std::string image_folder = config.input_folder + "/images", cam_folder = config.input_folder + "/cams";
     // 1. every view that some problem uses: decoded once (host threads), resized by PatchMatchInit's rule
     std::vector<char> needed(n, 0);
@@ -303,72 +308,109 @@ static void RunResident(const ConfigParams& config, std::vector<Scene>& Scenes, 
         all_u8 = all_u8 && im.u8.size() == im.px.size();
     }
     if (!W) return;
-    // 2. the per-GPU image cache
-    mpmvs_image_cache* cache = nullptr;
-    check(mpmvs_cache_create_fmt(device, W, H, n, all_u8 ? MPMVS_TEX_U8 : MPMVS_TEX_F32, &cache), "mpmvs_cache_create_fmt");
-    for (int i = 0; i < n; ++i) {
-        if (!needed[i]) continue;
-        const GrayImage& im = Scenes[i].image;
-        check(all_u8 ? mpmvs_cache_put_u8(cache, i, im.u8.data(), W, H) : mpmvs_cache_put(cache, i, im.px.data(), W, H), "mpmvs_cache_put");
-    }
-    // 3. one resident handle per reference image
-    std::vector<mpmvs_problem*> handles(n, nullptr);
-    std::vector<int> refs;
-    for (int i = 0; i < n; ++i) {
-        if (!Scenes[i].estimate) continue;
-        refs.push_back(i);
-        check(mpmvs_create(device, nullptr, &handles[i]), "mpmvs_create");
-        std::vector<Camera> pc;
-        for (int id : Scenes[i].srcID) pc.push_back(cams[id]);
-        check(mpmvs_set_views_cached(handles[i], cache, (int)pc.size(), Scenes[i].srcID.data(), pc.data()), "mpmvs_set_views_cached");
-    }
-    // 4. depth maps of the previous pass, all images, in device memory (double-buffered: Jacobi)
+    // 2. reference images in contiguous blocks over the GPUs (as pipeline.shard_refs); per GPU: an image cache with the
+    //    views its problems use, one resident handle per reference image, and the depth maps of ALL images of the previous
+    //    pass (double-buffered: Jacobi)
+    const int G = (int)devices.size();
+    std::vector<int> refs, owner(n, -1);
+    for (int i = 0; i < n; ++i) if (Scenes[i].estimate) refs.push_back(i);
+    const size_t block = (refs.size() + G - 1) / G;
+    for (size_t k = 0; k < refs.size(); ++k) owner[refs[k]] = (int)(k / block);
     const size_t wh = (size_t)W * H;
-    float* depth_buf[2] = {nullptr, nullptr};
-    if (config.geom_iterations > 0)
-        for (float*& b : depth_buf) { cuda_ok(cudaMalloc((void**)&b, wh * 4 * n), "cudaMalloc"); cuda_ok(cudaMemset(b, 0, wh * 4 * n), "cudaMemset"); }
-    printf("resident set-up (decode, upload, handles): %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_setup).count());
+    struct Gpu { int dev = 0; mpmvs_image_cache* cache = nullptr; float* depth[2] = {nullptr, nullptr}; cudaStream_t copy = nullptr; std::vector<int> refs; };
+    std::vector<Gpu> gpus(G);
+    std::vector<mpmvs_problem*> handles(n, nullptr);
+    for (int g = 0; g < G; ++g) {
+        Gpu& U = gpus[g];
+        U.dev = devices[g];
+        cuda_ok(cudaSetDevice(U.dev), "cudaSetDevice");
+        for (int g2 = 0; g2 < G; ++g2) {                    // depth maps travel GPU to GPU (NVLink) when peer access is available
+            int can = 0;
+            if (g2 != g && cudaDeviceCanAccessPeer(&can, U.dev, devices[g2]) == cudaSuccess && can) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(devices[g2], 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) cuda_ok(e, "cudaDeviceEnablePeerAccess");
+                cudaGetLastError();
+            }
+        }
+        cuda_ok(cudaStreamCreateWithFlags(&U.copy, cudaStreamNonBlocking), "cudaStreamCreate");
+        std::vector<char> need_g(n, 0);
+        int count = 0;
+        for (int i : refs) if (owner[i] == g) { U.refs.push_back(i); for (int id : Scenes[i].srcID) if (!need_g[id]) { need_g[id] = 1; ++count; } }
+        if (U.refs.empty()) continue;
+        check(mpmvs_cache_create_fmt(U.dev, W, H, std::max(1, count), all_u8 ? MPMVS_TEX_U8 : MPMVS_TEX_F32, &U.cache), "mpmvs_cache_create_fmt");
+        for (int i = 0; i < n; ++i) {
+            if (!need_g[i]) continue;
+            const GrayImage& im = Scenes[i].image;
+            check(all_u8 ? mpmvs_cache_put_u8(U.cache, i, im.u8.data(), W, H) : mpmvs_cache_put(U.cache, i, im.px.data(), W, H), "mpmvs_cache_put");
+        }
+        for (int i : U.refs) {
+            check(mpmvs_create(U.dev, nullptr, &handles[i]), "mpmvs_create");
+            std::vector<Camera> pc;
+            for (int id : Scenes[i].srcID) pc.push_back(cams[id]);
+            check(mpmvs_set_views_cached(handles[i], U.cache, (int)pc.size(), Scenes[i].srcID.data(), pc.data()), "mpmvs_set_views_cached");
+        }
+        if (config.geom_iterations > 0)
+            for (float*& d : U.depth) { cuda_ok(cudaMalloc((void**)&d, wh * 4 * n), "cudaMalloc"); cuda_ok(cudaMemset(d, 0, wh * 4 * n), "cudaMemset"); }
+    }
+    for (const Gpu& U : gpus) { cuda_ok(cudaSetDevice(U.dev), "cudaSetDevice"); cuda_ok(cudaDeviceSynchronize(), "cudaDeviceSynchronize"); }
+    printf("resident set-up on %d GPU(s) (decode, upload, handles): %.3f s\n", G, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_setup).count());
 
     const auto t0 = std::chrono::steady_clock::now();
     int cur = 0;
-    auto run_pass = [&](int stage, bool geom, bool planar) {
-        std::atomic<size_t> next{0};
+    const bool exchange = config.geom_iterations > 0;
+    // `per_gpu` worker threads per GPU walk that GPU's images; fn(gpu, image) throws on error
+    auto for_all_images = [&](int per_gpu, const std::function<void(const Gpu&, int, int)>& fn) {
+        std::vector<std::atomic<size_t>> next(G);
+        for (auto& x : next) x = 0;
         std::atomic<bool> failed{false};
         std::string err;
         std::mutex err_m;
-        auto work = [&] {
-            for (size_t k; (k = next++) < refs.size();) {
-                const int i = refs[k];
-                mpmvs_problem* h = handles[i];
-                try {
-                    const uint64_t sd = seed + 1000003ULL * i + 7919ULL * stage;
-                    check(mpmvs_reset_params(h), "mpmvs_reset_params");                       // a fresh PatchMatchCUDA per call (cpp:516)
-                    check(mpmvs_set_geom_consistency_params(h, geom, planar), "mpmvs_set_geom_consistency_params");
-                    if (geom) {
-                        std::vector<const float*> dep;
-                        for (size_t j = 1; j < Scenes[i].srcID.size(); ++j) dep.push_back(depth_buf[cur] + wh * Scenes[i].srcID[j]);
-                        check(mpmvs_set_src_depths_device(h, dep.data(), nullptr), "mpmvs_set_src_depths_device");
-                    }
-                    check(mpmvs_run_async(h, sd), "mpmvs_run_async");
-                    if (planar) {
-                        check(mpmvs_set_planar_prior_params(h), "mpmvs_set_planar_prior_params");
-                        check(mpmvs_set_geom_consistency_params(h, 0, 1), "mpmvs_set_geom_consistency_params");
-                        check(mpmvs_build_prior(h, nullptr), "mpmvs_build_prior");           // blocks this thread only
-                        check(mpmvs_run_async(h, sd ^ 0x5DEECE66DULL), "mpmvs_run_async");
-                    }
-                    if (depth_buf[0]) check(mpmvs_export_depth_device(h, depth_buf[cur ^ 1] + wh * i, 0), "mpmvs_export_depth_device");
-                } catch (const std::exception& e) {
-                    std::lock_guard<std::mutex> l(err_m);
-                    err = e.what();
-                    failed = true;
-                }
-            }
-        };
         std::vector<std::thread> pool;
-        for (int t = 0; t < std::max(1, in_flight); ++t) pool.emplace_back(work);
+        for (int g = 0; g < G; ++g)
+            for (int t = 0; t < std::max(1, per_gpu); ++t)
+                pool.emplace_back([&, g, t, per_gpu] {
+                    const Gpu& U = gpus[g];
+                    cudaSetDevice(U.dev);
+                    for (size_t k; (k = next[g]++) < U.refs.size();) {
+                        try { fn(U, U.refs[k], g * std::max(1, per_gpu) + t); }
+                        catch (const std::exception& e) { std::lock_guard<std::mutex> l(err_m); err = e.what(); failed = true; }
+                    }
+                });
         for (std::thread& t : pool) t.join();
-        for (int i : refs) check(mpmvs_synchronize(handles[i]), "mpmvs_synchronize");
         if (failed) throw std::runtime_error(err);
+    };
+    auto run_pass = [&](int stage, bool geom, bool planar) {
+        for_all_images(in_flight, [&](const Gpu& U, int i, int) {
+            mpmvs_problem* h = handles[i];
+            const uint64_t sd = seed + 1000003ULL * i + 7919ULL * stage;
+            check(mpmvs_reset_params(h), "mpmvs_reset_params");                               // a fresh PatchMatchCUDA per call (cpp:516)
+            check(mpmvs_set_geom_consistency_params(h, geom, planar), "mpmvs_set_geom_consistency_params");
+            if (geom) {
+                std::vector<const float*> dep;
+                for (size_t j = 1; j < Scenes[i].srcID.size(); ++j) dep.push_back(U.depth[cur] + wh * Scenes[i].srcID[j]);
+                check(mpmvs_set_src_depths_device(h, dep.data(), nullptr), "mpmvs_set_src_depths_device");
+            }
+            check(mpmvs_run_async(h, sd), "mpmvs_run_async");
+            if (planar) {
+                check(mpmvs_set_planar_prior_params(h), "mpmvs_set_planar_prior_params");
+                check(mpmvs_set_geom_consistency_params(h, 0, 1), "mpmvs_set_geom_consistency_params");
+                check(mpmvs_build_prior(h, nullptr), "mpmvs_build_prior");                   // blocks this thread only
+                check(mpmvs_run_async(h, sd ^ 0x5DEECE66DULL), "mpmvs_run_async");
+            }
+            if (exchange) check(mpmvs_export_depth_device(h, U.depth[cur ^ 1] + wh * i, 0), "mpmvs_export_depth_device");
+        });
+        for (int i : refs) check(mpmvs_synchronize(handles[i]), "mpmvs_synchronize");
+        // all-gather by peer copies: every image's new depth map goes from its owner to the other GPUs' buffers
+        if (exchange && G > 1) {
+            for (const Gpu& U : gpus) {
+                cuda_ok(cudaSetDevice(U.dev), "cudaSetDevice");
+                for (int i : U.refs)
+                    for (const Gpu& V : gpus)
+                        if (V.dev != U.dev && V.depth[0])
+                            cuda_ok(cudaMemcpyPeerAsync(V.depth[cur ^ 1] + wh * i, V.dev, U.depth[cur ^ 1] + wh * i, U.dev, wh * 4, U.copy), "cudaMemcpyPeerAsync");
+            }
+            for (const Gpu& U : gpus) { cuda_ok(cudaSetDevice(U.dev), "cudaSetDevice"); cuda_ok(cudaStreamSynchronize(U.copy), "cudaStreamSynchronize"); }
+        }
         cur ^= 1;
     };
     const auto stamp = [&](const char* what) {
@@ -381,39 +423,42 @@ static void RunResident(const ConfigParams& config, std::vector<Scene>& Scenes, 
         stamp("geometric consistency pass");
     }
     printf("cost time is %.10f us\n", std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
-    // 5. results: pinned staging, split into the three maps of a result folder, files written in the background
-    {
-        std::atomic<size_t> next{0};
-        std::atomic<bool> failed{false};
-        auto work = [&] {
-            float *pl = nullptr, *co = nullptr;
-            if (cudaSetDevice(device) != cudaSuccess || cudaMallocHost((void**)&pl, wh * 16) != cudaSuccess ||
-                cudaMallocHost((void**)&co, wh * 4) != cudaSuccess) { failed = true; cudaFreeHost(pl); return; }
-            for (size_t k; (k = next++) < refs.size();) {
-                const int i = refs[k];
-                if (mpmvs_get_results_async(handles[i], pl, co, nullptr) != MPMVS_OK || mpmvs_synchronize(handles[i]) != MPMVS_OK) { failed = true; break; }
-                auto depths = std::make_shared<std::vector<float>>(wh), normals = std::make_shared<std::vector<float>>(wh * 3);
-                auto costs = std::make_shared<std::vector<float>>(co, co + wh);
-                float *dd = depths->data(), *nn = normals->data();
-                for (size_t q = 0; q < wh; ++q) { nn[3 * q] = pl[4 * q]; nn[3 * q + 1] = pl[4 * q + 1]; nn[3 * q + 2] = pl[4 * q + 2]; dd[q] = pl[4 * q + 3]; }
-                const std::string folder = config.output_folder + "/2333_" + id8(Scenes[i].refID);
-                mkdir(folder.c_str(), 0777);
-                SubmitDmb(folder + "/depths.dmb", H, W, 1, depths);
-                SubmitDmb(folder + "/normals.dmb", H, W, 3, normals);
-                SubmitDmb(folder + "/costs.dmb", H, W, 1, costs);
-                Scenes[i].depth = depths; Scenes[i].normal = normals; Scenes[i].cost = costs;
-            }
-            cudaFreeHost(pl); cudaFreeHost(co);
-        };
-        std::vector<std::thread> pool;
-        for (int t = 0; t < 4; ++t) pool.emplace_back(work);
-        for (std::thread& t : pool) t.join();
-        if (failed) throw std::runtime_error("resident pipeline: reading the results back failed");
+    // 3. results: pinned staging, split into the three maps of a result folder, files written in the background
+    const int collectors = G > 1 ? 2 : 4;
+    std::vector<float*> pin_planes(G * collectors, nullptr), pin_costs(G * collectors, nullptr);
+    for (int g = 0; g < G; ++g) {
+        cuda_ok(cudaSetDevice(gpus[g].dev), "cudaSetDevice");
+        for (int t = 0; t < collectors; ++t) {
+            cuda_ok(cudaMallocHost((void**)&pin_planes[g * collectors + t], wh * 16), "cudaMallocHost");
+            cuda_ok(cudaMallocHost((void**)&pin_costs[g * collectors + t], wh * 4), "cudaMallocHost");
+        }
     }
+    for_all_images(collectors, [&](const Gpu&, int i, int slot) {
+        float *pl = pin_planes[slot], *co = pin_costs[slot];
+        check(mpmvs_get_results_async(handles[i], pl, co, nullptr), "mpmvs_get_results_async");
+        check(mpmvs_synchronize(handles[i]), "mpmvs_synchronize");
+        auto depths = std::make_shared<std::vector<float>>(wh), normals = std::make_shared<std::vector<float>>(wh * 3);
+        auto costs = std::make_shared<std::vector<float>>(co, co + wh);
+        float *dd = depths->data(), *nn = normals->data();
+        for (size_t q = 0; q < wh; ++q) { nn[3 * q] = pl[4 * q]; nn[3 * q + 1] = pl[4 * q + 1]; nn[3 * q + 2] = pl[4 * q + 2]; dd[q] = pl[4 * q + 3]; }
+        const std::string folder = config.output_folder + "/2333_" + id8(Scenes[i].refID);
+        mkdir(folder.c_str(), 0777);
+        SubmitDmb(folder + "/depths.dmb", H, W, 1, depths);
+        SubmitDmb(folder + "/normals.dmb", H, W, 3, normals);
+        SubmitDmb(folder + "/costs.dmb", H, W, 1, costs);
+        Scenes[i].depth = depths; Scenes[i].normal = normals; Scenes[i].cost = costs;
+    });
     printf("results collected after %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
-    for (float* b : depth_buf) cudaFree(b);
+    for (float* b : pin_planes) cudaFreeHost(b);
+    for (float* b : pin_costs) cudaFreeHost(b);
     for (mpmvs_problem* h : handles) if (h) mpmvs_destroy(h);
-    mpmvs_cache_destroy(cache);
+    for (Gpu& U : gpus) {
+        cudaSetDevice(U.dev);
+        for (float* d : U.depth) cudaFree(d);
+        if (U.copy) cudaStreamDestroy(U.copy);
+        if (U.cache) mpmvs_cache_destroy(U.cache);
+    }
+    cudaSetDevice(devices[0]);
 }
 
 }  // namespace mpmvs
@@ -424,7 +469,7 @@ int main(int argc, char* argv[]) {
     uint64_t seed = 0x2333;
     int tex = MPMVS_TEX_F32;
     bool fusion = true, gpu_fusion = false, profile = false, resident = false;
-    int in_flight = 4, device = 0;
+    int in_flight = 4, device = 0, n_gpus = 1;
     for (int i = 1; i < argc; ++i) {
         if (!strcmp(argv[i], "--seed") && i + 1 < argc) seed = strtoull(argv[++i], nullptr, 0);
         else if (!strcmp(argv[i], "--tex") && i + 1 < argc) tex = !strcmp(argv[++i], "u8") ? MPMVS_TEX_U8 : MPMVS_TEX_F32;
@@ -434,6 +479,7 @@ int main(int argc, char* argv[]) {
         else if (!strcmp(argv[i], "--resident")) resident = true;
         else if (!strcmp(argv[i], "--in-flight") && i + 1 < argc) in_flight = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--gpus") && i + 1 < argc) n_gpus = atoi(argv[++i]);
         else yaml = argv[i];
     }
     try {
@@ -447,7 +493,9 @@ int main(int argc, char* argv[]) {
         const auto t0 = std::chrono::steady_clock::now();
         if (resident) {
             mkdir(config.output_folder.c_str(), 0777);
-            RunResident(config, Scenes, seed, tex, in_flight, device);
+            std::vector<int> devices;
+            for (int g = 0; g < std::max(1, n_gpus); ++g) devices.push_back(device + g);
+            RunResident(config, Scenes, seed, tex, in_flight, devices);
         } else {
             // stage 1: multi-scale-window PatchMatch (main.cpp:19-26)
             bool planar_prior = !config.geomPlanarPrior && config.planar_prior;

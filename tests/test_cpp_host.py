@@ -113,6 +113,30 @@ def test_main_resident_mode(tmp_path):
 
 
 @pytest.mark.gpu
+def test_main_resident_two_gpus(tmp_path):
+    """--resident --gpus 2: reference images sharded over two GPUs by one process, depth maps all-gathered with peer copies.
+    Bit-identical to the one-GPU run."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    build_main()
+    sc, root, yaml = write_scene(tmp_path, **{"Geometric consistency iterations": 2, "Planer prior": 0,
+                                              "Geometric consistency planer prior": 0})
+    out = os.path.join(root, "MPMVS")
+    res = {}
+    for g in (1, 2):
+        r = subprocess.run([MAIN, yaml, "--seed", "5", "--tex", "u8", "--no-fusion", "--resident", "--gpus", str(g)], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert f"resident set-up on {g} GPU(s)" in r.stdout
+        res[g] = [PKG.io_formats.read_dmb(os.path.join(out, f"2333_{i:08d}", name)) for i in range(sc.num_views) for name in ("depths.dmb", "normals.dmb", "costs.dmb")]
+    for a, b in zip(res[1], res[2]):
+        np.testing.assert_array_equal(a, b)
+    accs = [PKG.synth.accuracy_at(res[2][3 * i], sc.gt_depth[i])[2] for i in range(sc.num_views)]
+    assert np.median(accs) > 95
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("max_size", [3200, 200])
 def test_python_cli_matches_layout(tmp_path, max_size):
     """mp-mvs_b200/run.py: the sharded pipeline as a drop-in for main() over the same dense folder and YAML keys."""
