@@ -161,6 +161,36 @@ def measured_peaks() -> dict:
 
 
 # --------------------------------------------------------------------------------------------- arms
+TAKE_TURNS = os.environ.get("MPMVS_BENCH_TURNS", "1") != "0"
+
+
+class GpuTurn:
+    """FIFO ticket for whole Run()s on one GPU. Several reference images are in flight so that the device never waits for
+    the host (triangulation, copies); but two Run()s that share the SMs finish together, send their images into the host
+    stage together and leave the device idle together, and that lock-step is stable. Taking turns keeps the images out of
+    phase by construction: while one image's Run() has the device, the other does its host work."""
+
+    def __init__(self):
+        import threading
+
+        self.cv = threading.Condition()
+        self.next_ticket = 0
+        self.serving = 0
+
+    def __enter__(self):
+        with self.cv:
+            t = self.next_ticket
+            self.next_ticket += 1
+            self.cv.wait_for(lambda: self.serving == t)
+        return self
+
+    def __exit__(self, *exc):
+        with self.cv:
+            self.serving += 1
+            self.cv.notify_all()
+        return False
+
+
 def start_problem(pm, seed):
     """First half of ProcessProblem(geom=false, planar=true), /root/reference/src/PatchMatch.cpp:516-531: photometric Run()."""
     pm.reset_params()
@@ -179,7 +209,7 @@ def finish_problem(pm, seed, prof=None):
     return st
 
 
-def process_problems(handles, n_steps, seed0, upload=None, download=None, prof=None, streams=None):
+def process_problems(handles, n_steps, seed0, upload=None, download=None, prof=None, streams=None, trace=None):
     """n_steps reference images through ProcessProblem. Every handle is driven by its own host thread (the C ABI blocks
     only the calling thread and releases the GIL), image i goes to handle i mod len(handles). The handles' streams have
     different priorities, so the GPU serves the most urgent handle first and fills the gaps it leaves -- its host
@@ -188,16 +218,36 @@ def process_problems(handles, n_steps, seed0, upload=None, download=None, prof=N
     from concurrent.futures import ThreadPoolExecutor
 
     stats = [None] * n_steps
+    turn = GpuTurn() if (len(handles) > 1 and prof is None and TAKE_TURNS) else None
+
+    def timed(name, k, i, fn, *a):
+        if trace is None:
+            return fn(*a)
+        t = time.time()
+        r = fn(*a)
+        trace.append((k, i, name, t, time.time()))      # host-side duration of the call: shows which C-ABI calls block
+        return r
 
     def worker(k):
         pm = handles[k]
         for i in range(k, n_steps, len(handles)):
             if upload is not None:
-                upload(pm)
-            start_problem(pm, seed0 + 2 * i)
-            stats[i] = finish_problem(pm, seed0 + 2 * i, prof)
+                timed("upload", k, i, upload, pm)
+            if turn is None:
+                timed("start", k, i, start_problem, pm, seed0 + 2 * i)
+                stats[i] = timed("finish", k, i, finish_problem, pm, seed0 + 2 * i, prof)
+            else:
+                with turn:                                   # photometric Run()
+                    timed("start", k, i, start_problem, pm, seed0 + 2 * i)
+                    timed("wait", k, i, pm.synchronize)
+                pm.set_planar_prior_params()
+                pm.set_geom_consistency_params(False, True)
+                stats[i] = timed("prior", k, i, pm.build_prior)      # vertex pick, host triangulation, rasterisation
+                with turn:                                   # planar-prior Run()
+                    timed("run2", k, i, pm.run_async, seed0 + 2 * i + 1)
+                    timed("wait2", k, i, pm.synchronize)
             if download is not None:
-                download(pm)
+                timed("download", k, i, download, pm)
             if prof is not None:        # sequential profiling pass: read the prior run's events too
                 pm.synchronize()
                 prof.append(pm.last_run_profile(timing=prof.timing, count=prof.count))
@@ -290,8 +340,17 @@ def run_ours(args, rank, world, local_rank, prob, barrier, allmax):
     sync_all()
     barrier(); torch.cuda.synchronize()
     t0 = time.time()
-    process_problems(handles, args.steps, seed + 200, upload, download, streams=streams)
+    trace = [] if args.trace else None
+    skip = os.environ.get("MPMVS_E2E_SKIP", "") if args.trace else ""      # diagnostic only: isolate the cost of either copy
+    if skip:
+        print(f"[diagnostic] e2e region without: {skip} -- not a valid e2e number", file=sys.stderr)
+    process_problems(handles, args.steps, seed + 200, None if "upload" in skip else upload, None if "download" in skip else download,
+                     streams=streams, trace=trace)
     sync_all()
+    if trace:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"e2e_trace_rank{rank}.json"), "w") as fh:
+            json.dump({"t0": t0, "t_end": time.time(), "calls": sorted(trace, key=lambda c: c[3])}, fh)
     torch.cuda.synchronize()
     e2e_s = allmax(time.time() - t0)
     barrier()
@@ -466,6 +525,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="eth3d")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--trace", action="store_true", help="write the host-side call timeline of the e2e region to gpurun_out/")
     ap.add_argument("--in-flight", type=int, default=2, help="reference images kept in flight per GPU (1 = the reference's sequential order)")
     ap.add_argument("--tex", default="u8", choices=["f32", "f16", "u8"], help="storage format of the views in HBM")
     args = ap.parse_args()

@@ -887,16 +887,20 @@ int mpmvs_pick_vertices(mpmvs_problem* p, int geom_variant, int* xy_out, int max
 int mpmvs_prior_from_triangles(mpmvs_problem* p, const int* xy, int n_vertices, const int* tris, int n_tris, int* n_prior_pixels) {
     if (!p || p->n < 2 || n_vertices < 0 || n_tris < 0 || (n_tris > 0 && (!xy || !tris))) return MPMVS_E_ARG;
     CK(cudaSetDevice(p->device));
+    // Grow with headroom: the counts differ a little from image to image and from pass to pass, and every cudaFree here
+    // would wait for the whole device -- i.e. for the runs of the other images in flight -- before this image can go on.
     if ((size_t)n_vertices > p->vtx_cap) {
+        const size_t cap = (size_t)n_vertices + (size_t)n_vertices / 2 + 1024;
         cudaFree(p->d_vxy); p->d_vxy = nullptr; p->vtx_cap = 0;
-        CK(cudaMalloc((void**)&p->d_vxy, sizeof(int2) * (size_t)n_vertices));
-        p->vtx_cap = (size_t)n_vertices;
+        CK(cudaMalloc((void**)&p->d_vxy, sizeof(int2) * cap));
+        p->vtx_cap = cap;
     }
     if ((size_t)n_tris > p->tri_cap) {
+        const size_t cap = (size_t)n_tris + (size_t)n_tris / 2 + 2048;
         cudaFree(p->d_tris); cudaFree(p->d_tri_planes); p->d_tris = nullptr; p->d_tri_planes = nullptr; p->tri_cap = 0;
-        CK(cudaMalloc((void**)&p->d_tris, sizeof(int3) * (size_t)n_tris));
-        CK(cudaMalloc((void**)&p->d_tri_planes, sizeof(pm_f4) * (size_t)n_tris));
-        p->tri_cap = (size_t)n_tris;
+        CK(cudaMalloc((void**)&p->d_tris, sizeof(int3) * cap));
+        CK(cudaMalloc((void**)&p->d_tri_planes, sizeof(pm_f4) * cap));
+        p->tri_cap = cap;
     }
     if (!p->d_prior_count) CK(cudaMalloc((void**)&p->d_prior_count, sizeof(unsigned int)));
     if (n_vertices) CK(cudaMemcpyAsync(p->d_vxy, xy, sizeof(int2) * (size_t)n_vertices, cudaMemcpyHostToDevice, p->stream));
