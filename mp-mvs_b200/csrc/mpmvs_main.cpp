@@ -469,7 +469,7 @@ int main(int argc, char* argv[]) {
     uint64_t seed = 0x2333;
     int tex = MPMVS_TEX_F32;
     bool fusion = true, gpu_fusion = false, profile = false, resident = false;
-    int in_flight = 4, device = 0, n_gpus = 1;
+    int in_flight = 8, device = 0, n_gpus = 1;   // host threads per GPU: the triangulation of the planar prior (up to 0.4 s per image) is host work
     for (int i = 1; i < argc; ++i) {
         if (!strcmp(argv[i], "--seed") && i + 1 < argc) seed = strtoull(argv[++i], nullptr, 0);
         else if (!strcmp(argv[i], "--tex") && i + 1 < argc) tex = !strcmp(argv[++i], "u8") ? MPMVS_TEX_U8 : MPMVS_TEX_F32;

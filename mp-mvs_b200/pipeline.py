@@ -49,7 +49,7 @@ class PipelineConfig:
     geom_iterations: int = 2          # "Geometric consistency iterations"
     planar_prior: bool = False        # "Planer prior"
     geom_planar_prior: bool = False   # "Geometric consistency planer prior"
-    in_flight: int = 4                # reference images a rank keeps in flight (host threads; the C ABI releases the GIL)
+    in_flight: int = 8                # reference images a rank keeps in flight (host threads; the C ABI releases the GIL)
     max_src: int = 20                 # "Max source images num"
     seed: int = 0
     tex_format: int = 2               # capi.TEX_U8: views are 8-bit grey levels as decoded from the JPEGs

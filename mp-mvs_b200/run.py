@@ -105,10 +105,15 @@ def load_scene(cfg: dict, rank: int, world: int):
     by_ref = {e.ref_id: e for e in entries if e.estimate}
     need = sorted({i for r in mine for i in by_ref[r].src_ids[: 1 + int(cfg["Max source images num"])]} | set(refs[:1]))
     cams, images = {}, {}
+    # decode on host threads (cv2 releases the GIL): the reference decodes every view again for every problem that uses it
+    from concurrent.futures import ThreadPoolExecutor
+
+    with ThreadPoolExecutor(min(16, os.cpu_count() or 1)) as ex:
+        decoded = dict(zip(need, ex.map(lambda i: load_image(os.path.join(inp, "images"), i, int(cfg["Max image size"])), need)))
     for i in sorted(set(refs) | set(need)):
         cam = io_formats.read_cam(os.path.join(inp, "cams", f"{i:08d}_cam.txt"))
         if i in need:
-            img, sx, sy = load_image(os.path.join(inp, "images"), i, int(cfg["Max image size"]))
+            img, sx, sy = decoded[i]
             images[i] = img
             cam.K = cam.K.copy()
             cam.K[0, 0] *= sx; cam.K[0, 2] *= sx; cam.K[1, 1] *= sy; cam.K[1, 2] *= sy
@@ -126,7 +131,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("config")
     ap.add_argument("--seed", type=int, default=0x2333)
-    ap.add_argument("--in-flight", type=int, default=4)
+    ap.add_argument("--in-flight", type=int, default=8, help="reference images in flight per GPU (host threads: the planar-prior triangulation is host work)")
     ap.add_argument("--fusion", type=int, default=1, help="fuse the depth maps on rank 0's GPU and write MPMVS_model.ply")
     args = ap.parse_args()
     import torch

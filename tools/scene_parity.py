@@ -51,6 +51,10 @@ t = time.time()
 stats = p.run()
 t_ours = time.time() - t
 ours = p.results()
+prior_stats = [p.engines[r].prior_stats for r in p.my_refs if getattr(p.engines[r], "prior_stats", None)]
+if prior_stats:
+    print("prior stage per image (last pass with a prior): vertices", [s["n_vertices"] for s in prior_stats], "pick ms", [round(s["pick_ms"], 1) for s in prior_stats],
+          "delaunay ms", [round(s["delaunay_ms"], 1) for s in prior_stats], "raster ms", [round(s["raster_ms"], 1) for s in prior_stats], flush=True)
 p.destroy()
 print("ours:", [(s.name, round(s.device_ms, 1), round(s.exchange_ms, 1)) for s in stats], f"total {t_ours:.2f} s", flush=True)
 
