@@ -164,33 +164,6 @@ def measured_peaks() -> dict:
 TAKE_TURNS = os.environ.get("MPMVS_BENCH_TURNS", "1") != "0"
 
 
-class GpuTurn:
-    """FIFO ticket for whole Run()s on one GPU. Several reference images are in flight so that the device never waits for
-    the host (triangulation, copies); but two Run()s that share the SMs finish together, send their images into the host
-    stage together and leave the device idle together, and that lock-step is stable. Taking turns keeps the images out of
-    phase by construction: while one image's Run() has the device, the other does its host work."""
-
-    def __init__(self):
-        import threading
-
-        self.cv = threading.Condition()
-        self.next_ticket = 0
-        self.serving = 0
-
-    def __enter__(self):
-        with self.cv:
-            t = self.next_ticket
-            self.next_ticket += 1
-            self.cv.wait_for(lambda: self.serving == t)
-        return self
-
-    def __exit__(self, *exc):
-        with self.cv:
-            self.serving += 1
-            self.cv.notify_all()
-        return False
-
-
 def start_problem(pm, seed):
     """First half of ProcessProblem(geom=false, planar=true), /root/reference/src/PatchMatch.cpp:516-531: photometric Run()."""
     pm.reset_params()
@@ -218,6 +191,8 @@ def process_problems(handles, n_steps, seed0, upload=None, download=None, prof=N
     from concurrent.futures import ThreadPoolExecutor
 
     stats = [None] * n_steps
+    from mpmvs_b200.pipeline import GpuTurn     # whole Run()s take turns on the device (see its docstring)
+
     turn = GpuTurn() if (len(handles) > 1 and prof is None and TAKE_TURNS) else None
 
     def timed(name, k, i, fn, *a):

@@ -19,6 +19,7 @@
 #include <atomic>
 #include <cfloat>
 #include <chrono>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -244,6 +245,32 @@ size_t RunFusionGPU(const ConfigParams& config, std::vector<Scene>& Scenes) {
 }
 
 // ------------------------------------------------------------------------------------------------ resident pipeline
+// FIFO ticket for whole Run()s on one GPU. Several reference images are in flight so that the device never waits for the
+// host (triangulation, copies); but Run()s that share the SMs finish together, send their images into the host stage
+// together and leave the device idle together, and that lock-step is stable. Taking turns keeps the images out of phase:
+// while one image's Run() has the device, the others do their host work (pipeline.GpuTurn).
+class GpuTurn {
+  public:
+    void acquire() {
+        std::unique_lock<std::mutex> l(m_);
+        const uint64_t t = next_++;
+        cv_.wait(l, [&] { return serving_ == t; });
+    }
+    void release() {
+        { std::lock_guard<std::mutex> l(m_); ++serving_; }
+        cv_.notify_all();
+    }
+  private:
+    std::mutex m_;
+    std::condition_variable cv_;
+    uint64_t next_ = 0, serving_ = 0;
+};
+struct TurnGuard {
+    explicit TurnGuard(GpuTurn& t) : t_(t) { t_.acquire(); }
+    ~TurnGuard() { t_.release(); }
+    GpuTurn& t_;
+};
+
 static void cuda_ok(cudaError_t e, const char* what) {
     if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
 }
@@ -379,6 +406,7 @@ static void RunResident(const ConfigParams& config, std::vector<Scene>& Scenes, 
         for (std::thread& t : pool) t.join();
         if (failed) throw std::runtime_error(err);
     };
+    std::vector<GpuTurn> turns(G);
     auto run_pass = [&](int stage, bool geom, bool planar) {
         for_all_images(in_flight, [&](const Gpu& U, int i, int) {
             mpmvs_problem* h = handles[i];
@@ -390,12 +418,21 @@ static void RunResident(const ConfigParams& config, std::vector<Scene>& Scenes, 
                 for (size_t j = 1; j < Scenes[i].srcID.size(); ++j) dep.push_back(U.depth[cur] + wh * Scenes[i].srcID[j]);
                 check(mpmvs_set_src_depths_device(h, dep.data(), nullptr), "mpmvs_set_src_depths_device");
             }
-            check(mpmvs_run_async(h, sd), "mpmvs_run_async");
+            GpuTurn& turn = turns[&U - gpus.data()];
+            if (planar) {           // a host stage follows: whole Run()s take turns (see GpuTurn)
+                TurnGuard g(turn);
+                check(mpmvs_run_async(h, sd), "mpmvs_run_async");
+                check(mpmvs_synchronize(h), "mpmvs_synchronize");
+            } else {                // no host stage: runs of different images share the device and fill each other's kernel tails
+                check(mpmvs_run_async(h, sd), "mpmvs_run_async");
+            }
             if (planar) {
                 check(mpmvs_set_planar_prior_params(h), "mpmvs_set_planar_prior_params");
                 check(mpmvs_set_geom_consistency_params(h, 0, 1), "mpmvs_set_geom_consistency_params");
-                check(mpmvs_build_prior(h, nullptr), "mpmvs_build_prior");                   // blocks this thread only
+                check(mpmvs_build_prior(h, nullptr), "mpmvs_build_prior");                   // host triangulation: blocks this thread only
+                TurnGuard g(turn);
                 check(mpmvs_run_async(h, sd ^ 0x5DEECE66DULL), "mpmvs_run_async");
+                check(mpmvs_synchronize(h), "mpmvs_synchronize");
             }
             if (exchange) check(mpmvs_export_depth_device(h, U.depth[cur ^ 1] + wh * i, 0), "mpmvs_export_depth_device");
         });

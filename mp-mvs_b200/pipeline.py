@@ -64,6 +64,41 @@ class PassStats:
     n_refs: int = 0
 
 
+class GpuTurn:
+    """FIFO ticket for whole Run()s on one GPU. Several reference images are in flight so that the device never waits for
+    the host (triangulation, copies); but Run()s that share the SMs finish together, send their images into the host stage
+    together and leave the device idle together, and that lock-step is stable. Taking turns keeps the images out of phase
+    by construction: while one image's Run() has the device, the others do their host work."""
+
+    def __init__(self):
+        import threading
+
+        self.cv = threading.Condition()
+        self.next_ticket = 0
+        self.serving = 0
+
+    def __enter__(self):
+        with self.cv:
+            t = self.next_ticket
+            self.next_ticket += 1
+            self.cv.wait_for(lambda: self.serving == t)
+        return self
+
+    def __exit__(self, *exc):
+        with self.cv:
+            self.serving += 1
+            self.cv.notify_all()
+        return False
+
+
+class _NoTurn:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
 class CudaEngine:
     """One reference image on one GPU: a resident `mpmvs_problem` (capi.PatchMatch)."""
 
@@ -74,20 +109,27 @@ class CudaEngine:
         self.pm.set_problem_cached(cache, list(ids), cams_packed)
         self.prior_stats = None
 
-    def process(self, seed: int, geom: bool, planar: bool, src_depth_ptrs: Optional[Sequence[int]] = None):
+    def process(self, seed: int, geom: bool, planar: bool, src_depth_ptrs: Optional[Sequence[int]] = None, turn=None):
         """The compute of one ProcessProblem(geom, planar) call (PatchMatch.cpp:516-609) on the resident state:
-        Run(); if planar: planar-prior stage + planar-prior Run(). Returns with the last run still in flight."""
+        Run(); if planar: planar-prior stage + planar-prior Run(). With a `turn` (GpuTurn) every Run() waits for its turn on
+        the device and is complete on return; without, the last run is still in flight on return."""
         pm = self.pm
         pm.reset_params()                                   # a fresh PatchMatchCUDA object per call (PatchMatch.cpp:516)
         pm.set_geom_consistency_params(geom, planar)
         if geom:
             pm.set_src_depths_device(list(src_depth_ptrs))
-        pm.run_async(seed)
+        with (turn or _NoTurn()):
+            pm.run_async(seed)
+            if turn is not None:
+                pm.synchronize()
         if planar:
             pm.set_planar_prior_params()
             pm.set_geom_consistency_params(False, True)
             self.prior_stats = pm.build_prior()             # blocks this host thread only
-            pm.run_async(seed ^ 0x5DEECE66D)
+            with (turn or _NoTurn()):
+                pm.run_async(seed ^ 0x5DEECE66D)
+                if turn is not None:
+                    pm.synchronize()
 
     def export_depth(self, dst_tensor):
         self.pm.export_depth_device(dst_tensor.data_ptr(), dst_tensor.stride(0) * 4)
@@ -216,13 +258,19 @@ class DensePipeline:
         """One ProcessProblem per reference image of this rank, `in_flight` of them at a time on host threads."""
         from concurrent.futures import ThreadPoolExecutor
 
+        # passes with a host stage between two Run()s (the planar prior): whole Run()s take turns on the device (GpuTurn).
+        # Without a host stage nothing can leave the device idle, and runs sharing it fill each other's kernel tails
+        # (measured: DTU-shaped 49 views 5.62 s shared, 5.88 s with turns). Test engines have no device.
+        turn = GpuTurn() if (planar and self.engine_factory is None and self.cfg.in_flight > 1 and len(self.my_refs) > 1) else None
+        extra = {"turn": turn} if turn is not None else {}
+
         def one(ref):
             seed = stage_seed(self.cfg.seed, ref, stage)
             if geom:
                 views = [prev[self.slot[i]] for i in self.problem_ids(ref)[1:]]
-                self.engines[ref].process(seed, True, planar, [v.data_ptr() for v in views] if self.tdev.type == "cuda" else views)
+                self.engines[ref].process(seed, True, planar, [v.data_ptr() for v in views] if self.tdev.type == "cuda" else views, **extra)
             else:
-                self.engines[ref].process(seed, False, planar)
+                self.engines[ref].process(seed, False, planar, **extra)
 
         t0 = self._tick()
         if self.cfg.in_flight > 1 and len(self.my_refs) > 1:
@@ -277,166 +325,6 @@ class DensePipeline:
                 futs.append(ex.submit(write, ref, planes, costs))
             for f in futs:
                 f.result()
-
-    def destroy(self):
-        self.pm.destroy()
-
-
-class DensePipeline:
-    """entries: io_formats.SceneEntry list (pair.txt); cams: id -> io_formats.Camera; images: id -> uint8/float32 (H, W)."""
-
-    def __init__(self, entries, cams: Dict[int, object], images: Dict[int, np.ndarray], cfg: PipelineConfig, rank: int = 0,
-                 world: int = 1, device: int = 0, dist=None, engine_factory: Optional[Callable] = None, torch_device=None):
-        import torch
-
-        from . import io_formats
-
-        self.torch = torch
-        self.io = io_formats
-        self.cfg, self.rank, self.world, self.device, self.dist = cfg, rank, world, device, dist
-        self.entries = {e.ref_id: e for e in entries if e.estimate}
-        self.ref_ids = sorted(self.entries)
-        self.my_refs = shard_refs(self.ref_ids, rank, world)
-        self.block = block_size(len(self.ref_ids), world)
-        self.cams, self.images = cams, images
-        self.tdev = torch_device if torch_device is not None else torch.device("cuda", device)
-        self.engine_factory = engine_factory
-        self.engines: Dict[int, object] = {}
-        self.stats: List[PassStats] = []
-        any_cam = cams[self.ref_ids[0]]
-        self.H, self.W = int(any_cam.height), int(any_cam.width)
-        for i in self.ref_ids:
-            if (int(cams[i].height), int(cams[i].width)) != (self.H, self.W):
-                raise ValueError("the sharded pipeline requires equally sized views (one all-gather buffer)")
-        # slot of an image in the gathered buffer: rank-major, then position inside the rank's block
-        self.slot = {}
-        for r in range(world):
-            for k, ref in enumerate(shard_refs(self.ref_ids, r, world)):
-                self.slot[ref] = r * self.block + k
-        self.gathered = None          # [world * block, H, W] float32: depth maps of the previous pass
-        self.cache = None
-
-    # ------------------------------------------------------------------------------------------ set-up
-    def problem_ids(self, ref: int) -> List[int]:
-        ids = self.entries[ref].src_ids          # src_ids[0] == ref (GenerateSampleList, PatchMatch.cpp:84)
-        return [ids[0]] + list(ids[1:1 + self.cfg.max_src])
-
-    def setup(self):
-        need = sorted({i for ref in self.my_refs for i in self.problem_ids(ref)})
-        if self.engine_factory is None:
-            from . import capi
-
-            self.cache = capi.ImageCache(self.device, self.W, self.H, max(1, len(need)), self.cfg.tex_format)
-            for i in need:
-                self.cache.put(i, self.images[i])
-        for ref in self.my_refs:
-            ids = self.problem_ids(ref)
-            packed = self.io.pack_cameras([self.cams[i] for i in ids])
-            if self.engine_factory is None:
-                self.engines[ref] = CudaEngine(self.device, self.cache, ids, packed)
-            else:
-                self.engines[ref] = self.engine_factory(ids, [self.images[i] for i in ids], packed)
-        return len(need)
-
-    # ------------------------------------------------------------------------------------------ exchange
-    def _exchange(self, st: PassStats):
-        """All-gather of this pass's depth maps: rank r fills block r of a fresh [world*block, H, W] buffer."""
-        torch = self.torch
-        t0 = self._tick()
-        mine = torch.zeros((self.block, self.H, self.W), dtype=torch.float32, device=self.tdev)
-        self._sync_torch()             # the engines write on their own streams: the zero-fill must have landed
-        for k, ref in enumerate(self.my_refs):
-            self.engines[ref].export_depth(mine[k])
-        for ref in self.my_refs:
-            self.engines[ref].synchronize()
-        if self.world > 1:
-            out = torch.empty((self.world * self.block, self.H, self.W), dtype=torch.float32, device=self.tdev)
-            self.dist.all_gather_into_tensor(out, mine)
-            self._sync_torch()         # ... and the gathered maps must be complete before the engines' streams read them
-        else:
-            out = mine
-        self.gathered = out            # the previous buffer is dropped only now: Jacobi double buffering
-        st.exchange_ms = self._tock(t0)
-
-    def _sync_torch(self):
-        if self.tdev.type == "cuda":
-            self.torch.cuda.synchronize(self.tdev)
-
-    def _tick(self):
-        if self.tdev.type == "cuda":
-            e = self.torch.cuda.Event(enable_timing=True)
-            e.record()
-            return e
-        import time
-
-        return time.time()
-
-    def _tock(self, t0) -> float:
-        if self.tdev.type == "cuda":
-            e = self.torch.cuda.Event(enable_timing=True)
-            e.record()
-            e.synchronize()
-            return float(t0.elapsed_time(e))
-        import time
-
-        return (time.time() - t0) * 1e3
-
-    # ------------------------------------------------------------------------------------------ passes
-    def _run_pass(self, st: PassStats, stage: int, geom: bool, planar: bool, prev=None):
-        """One ProcessProblem per reference image of this rank, `in_flight` of them at a time on host threads."""
-        from concurrent.futures import ThreadPoolExecutor
-
-        def one(ref):
-            seed = stage_seed(self.cfg.seed, ref, stage)
-            if geom:
-                views = [prev[self.slot[i]] for i in self.problem_ids(ref)[1:]]
-                self.engines[ref].process(seed, True, planar, [v.data_ptr() for v in views] if self.tdev.type == "cuda" else views)
-            else:
-                self.engines[ref].process(seed, False, planar)
-
-        t0 = self._tick()
-        if self.cfg.in_flight > 1 and len(self.my_refs) > 1:
-            with ThreadPoolExecutor(self.cfg.in_flight) as ex:
-                list(ex.map(one, self.my_refs))
-        else:
-            for ref in self.my_refs:
-                one(ref)
-        for ref in self.my_refs:
-            self.engines[ref].synchronize()
-        st.device_ms = self._tock(t0)
-
-    def run(self):
-        """The stage schedule of main() (main.cpp:20-41) over this rank's reference images."""
-        if not self.engines:
-            self.setup()
-        cfg = self.cfg
-        st = PassStats("photometric" + (" + planar prior" if cfg.planar_prior and not cfg.geom_planar_prior else ""), n_refs=len(self.my_refs))
-        self._run_pass(st, 0, False, cfg.planar_prior and not cfg.geom_planar_prior)
-        if cfg.geom_iterations > 0:
-            self._exchange(st)
-        self.stats.append(st)
-        for g in range(cfg.geom_iterations):
-            planar = cfg.geom_planar_prior and g != cfg.geom_iterations - 1
-            st = PassStats(f"geometric {g}" + (" + planar prior" if planar else ""), n_refs=len(self.my_refs))
-            self._run_pass(st, 1 + g, True, planar, self.gathered)
-            if g + 1 < cfg.geom_iterations:
-                self._exchange(st)
-            self.stats.append(st)
-        return self.stats
-
-    def results(self) -> Dict[int, tuple]:
-        return {ref: self.engines[ref].result() for ref in self.my_refs}
-
-    def write_results(self, out_folder: str):
-        """<out>/MPMVS/2333_%08d/{depths,normals,costs}.dmb (PatchMatch.cpp:510-513,620-633)."""
-        import os
-
-        for ref, (planes, costs) in self.results().items():
-            d = self.io.result_dir(out_folder, ref)
-            os.makedirs(d, exist_ok=True)
-            self.io.write_dmb(os.path.join(d, "depths.dmb"), np.ascontiguousarray(planes[..., 3]))
-            self.io.write_dmb(os.path.join(d, "normals.dmb"), np.ascontiguousarray(planes[..., :3]))
-            self.io.write_dmb(os.path.join(d, "costs.dmb"), costs)
 
     def destroy(self):
         for e in self.engines.values():
