@@ -347,7 +347,7 @@ static void RunResident(const ConfigParams& config, std::vector<Scene>& Scenes, 
     struct Gpu { int dev = 0; mpmvs_image_cache* cache = nullptr; float* depth[2] = {nullptr, nullptr}; cudaStream_t copy = nullptr; std::vector<int> refs; };
     std::vector<Gpu> gpus(G);
     std::vector<mpmvs_problem*> handles(n, nullptr);
-    for (int g = 0; g < G; ++g) {
+    auto setup_gpu = [&](int g) {
         Gpu& U = gpus[g];
         U.dev = devices[g];
         cuda_ok(cudaSetDevice(U.dev), "cudaSetDevice");
@@ -363,7 +363,7 @@ static void RunResident(const ConfigParams& config, std::vector<Scene>& Scenes, 
         std::vector<char> need_g(n, 0);
         int count = 0;
         for (int i : refs) if (owner[i] == g) { U.refs.push_back(i); for (int id : Scenes[i].srcID) if (!need_g[id]) { need_g[id] = 1; ++count; } }
-        if (U.refs.empty()) continue;
+        if (U.refs.empty()) return;
         check(mpmvs_cache_create_fmt(U.dev, W, H, std::max(1, count), all_u8 ? MPMVS_TEX_U8 : MPMVS_TEX_F32, &U.cache), "mpmvs_cache_create_fmt");
         for (int i = 0; i < n; ++i) {
             if (!need_g[i]) continue;
@@ -378,6 +378,14 @@ static void RunResident(const ConfigParams& config, std::vector<Scene>& Scenes, 
         }
         if (config.geom_iterations > 0)
             for (float*& d : U.depth) { cuda_ok(cudaMalloc((void**)&d, wh * 4 * n), "cudaMalloc"); cuda_ok(cudaMemset(d, 0, wh * 4 * n), "cudaMemset"); }
+    };
+    {   // one host thread per GPU: context creation, uploads and allocations of different devices overlap
+        std::vector<std::thread> pool;
+        std::vector<std::string> errs(G);
+        for (int g = 0; g < G; ++g)
+            pool.emplace_back([&, g] { try { setup_gpu(g); } catch (const std::exception& e) { errs[g] = e.what(); } });
+        for (std::thread& t : pool) t.join();
+        for (const std::string& e : errs) if (!e.empty()) throw std::runtime_error(e);
     }
     for (const Gpu& U : gpus) { cuda_ok(cudaSetDevice(U.dev), "cudaSetDevice"); cuda_ok(cudaDeviceSynchronize(), "cudaDeviceSynchronize"); }
     printf("resident set-up on %d GPU(s) (decode, upload, handles): %.3f s\n", G, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_setup).count());
