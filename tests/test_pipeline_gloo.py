@@ -112,3 +112,40 @@ def test_two_ranks_match_one_rank(tmp_path, oracle_cpu):
     photo = p0.results()
     p0.destroy()
     assert any(not np.array_equal(photo[r][0], single[r][0]) for r in single)
+
+
+def test_gpu_turn_is_fifo():
+    """pipeline.GpuTurn: whole Run()s take turns on a GPU in the order the host threads asked for them."""
+    import threading
+    import time
+
+    from mpmvs_b200.pipeline import GpuTurn
+
+    turn, order, inside = GpuTurn(), [], []
+    gate = threading.Event()
+
+    def worker(k):
+        gate.wait()
+        time.sleep(0.01 * k)                 # ask in a known order
+        with turn:
+            inside.append(k)
+            assert len(inside) == 1          # exclusive
+            time.sleep(0.02)
+            order.append(k)
+            inside.pop()
+
+    ts = [threading.Thread(target=worker, args=(k,)) for k in range(6)]
+    for t in ts:
+        t.start()
+    gate.set()
+    for t in ts:
+        t.join()
+    assert order == list(range(6))
+    # an exception inside a turn releases it
+    try:
+        with turn:
+            raise ValueError("boom")
+    except ValueError:
+        pass
+    with turn:
+        pass
