@@ -9,13 +9,13 @@
 //
 // Kernels:
 //   pm_sky_upsample_kernel   cv::resize INTER_LINEAR on CV_32FC1 (pixel-centre mapping, source index clamped)
-//   pm_sky_filter_kernel     one thread per pixel; the (tile + 18 px halo) of {b, g, r, mask} is staged once in shared
-//                            memory as float4, so a tap is one 16-byte shared load, 2 MUFU (sqrt, ex2) and ~12 FP32
-//                            instead of the reference's four uncoalesced global loads and three int->float conversions.
-//                            Taps are accumulated in the reference's order (x offset outer, y offset inner): the sums are
-//                            the same floats the reference kernel adds in the same sequence.
-// Bound: 1369 taps/pixel x (1 LDS.128 + 2 MUFU): shared-memory bandwidth (128 B/clk/SM -> 4 clk per warp-tap) and the
-// MUFU pipe (16 lanes/clk -> 4 clk per warp-tap) tie; HBM traffic is 11 B/pixel and irrelevant.
+//   pm_sky_filter_kernel     two vertically adjacent pixels per thread; the (32 x 32 tile + 18 px halo) of {b, g, r, mask} is
+//                            staged once in shared memory as float4, so two taps share one 16-byte shared load, and a tap
+//                            costs 2 MUFU (sqrt, ex2) and ~12 FP32 instead of the reference's four uncoalesced global loads
+//                            and three int->float conversions. Taps are accumulated in the reference's order (x offset
+//                            outer, y offset inner): the sums are the same floats the reference kernel adds in sequence.
+// Bound: 1369 taps/pixel x 2 MUFU on the 16-lane XU pipe (4 clk per warp-tap); with one pixel per thread the shared-memory
+// pipe was the limiter (95 % of peak, profiles/r01_ncu_sky_filter.txt). HBM traffic is 11 B/pixel and irrelevant.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -27,10 +27,11 @@
 namespace {
 
 constexpr int SKY_R = 18;                       // half_windows, sky.cu:13
-constexpr int SKY_BW = 32, SKY_BH = 16;         // threads = pixels per block
+constexpr int SKY_BW = 32, SKY_BH = 16;         // threads per block
+constexpr int SKY_PH = 2 * SKY_BH;              // pixel rows per block: two per thread
 constexpr int SKY_TW = SKY_BW + 2 * SKY_R;      // 68
-constexpr int SKY_TH = SKY_BH + 2 * SKY_R;      // 52
-constexpr size_t SKY_SMEM = (size_t)SKY_TW * SKY_TH * sizeof(float4) + (2 * SKY_R + 1) * (2 * SKY_R + 1) * sizeof(float);
+constexpr int SKY_TH = SKY_PH + 2 * SKY_R;      // 68
+constexpr size_t SKY_SMEM = (size_t)SKY_TW * SKY_TH * sizeof(float4) + (2 * SKY_R + 1) * (2 * SKY_R + 2) * sizeof(float);
 
 // cv::resize(src, dst, Size(W, H), ..., INTER_LINEAR) for one float channel
 __global__ void __launch_bounds__(256) pm_sky_upsample_kernel(const float* __restrict__ src, int sw, int sh, float* __restrict__ dst,
@@ -56,13 +57,16 @@ __global__ void __launch_bounds__(256) pm_sky_upsample_kernel(const float* __res
     dst[(size_t)dy * W + dx] = __fadd_rn(__fmul_rn(top, 1.f - fy), __fmul_rn(bot, fy));
 }
 
+// Two vertically adjacent pixels per thread: tap (i, j) of pixel (x, y) and tap (i, j - 1) of pixel (x, y + 1) are the same
+// tile element, so one 16-byte shared load and one spatial-weight load serve two taps. Each pixel still adds its 1369 taps
+// in the reference's order.
 __global__ void __launch_bounds__(SKY_BW* SKY_BH) pm_sky_filter_kernel(const unsigned char* __restrict__ bgr, const float* __restrict__ mask,
                                                                        float* __restrict__ result, float* __restrict__ prob_out, int W,
                                                                        int H) {
     extern __shared__ float4 sky_smem[];
-    float4 (*tile)[SKY_TW] = reinterpret_cast<float4 (*)[SKY_TW]>(sky_smem);                        // {b, g, r, mask}; 56.6 KB
-    float (*spatial)[2 * SKY_R + 1] = reinterpret_cast<float (*)[2 * SKY_R + 1]>(sky_smem + SKY_TW * SKY_TH);   // 5.5 KB
-    const int x0 = blockIdx.x * SKY_BW, y0 = blockIdx.y * SKY_BH;
+    float4 (*tile)[SKY_TW] = reinterpret_cast<float4 (*)[SKY_TW]>(sky_smem);                        // {b, g, r, mask}; 74 KB
+    float (*spatial)[2 * SKY_R + 2] = reinterpret_cast<float (*)[2 * SKY_R + 2]>(sky_smem + SKY_TW * SKY_TH);   // 5.6 KB
+    const int x0 = blockIdx.x * SKY_BW, y0 = blockIdx.y * SKY_PH;
     const int tid = threadIdx.y * SKY_BW + threadIdx.x;
     for (int i = tid; i < SKY_TW * SKY_TH; i += SKY_BW * SKY_BH) {
         const int ty = i / SKY_TW, tx = i - ty * SKY_TW;
@@ -79,31 +83,48 @@ __global__ void __launch_bounds__(SKY_BW* SKY_BH) pm_sky_filter_kernel(const uns
         tile[ty][tx] = t;
     }
     const float sigma_spatial = 2.0 * 6.0 * 6.0, sigma_color = 2.0 * 2.0 * 2.0;     // sky.cu:9-10
-    for (int i = tid; i < (2 * SKY_R + 1) * (2 * SKY_R + 1); i += SKY_BW * SKY_BH) {
-        const int a = i / (2 * SKY_R + 1) - SKY_R, b = i % (2 * SKY_R + 1) - SKY_R;
+    for (int i = tid; i < (2 * SKY_R + 1) * (2 * SKY_R + 2); i += SKY_BW * SKY_BH) {
+        const int a = i / (2 * SKY_R + 2) - SKY_R, b = i % (2 * SKY_R + 2) - SKY_R;    // column b = SKY_R + 1 is padding
         spatial[a + SKY_R][b + SKY_R] = sqrt((float)(a * a + b * b)) / sigma_spatial;   // sky.cu:26-27, hypothesis-invariant
     }
     __syncthreads();
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    const int x = x0 + threadIdx.x, ly = 2 * threadIdx.y, y = y0 + ly;
     if (x >= W || y >= H) return;
-    const float4 c = tile[threadIdx.y + SKY_R][threadIdx.x + SKY_R];
-    float weight_sum = 0.0f, prob = 0.0f;
+    const float4 c0 = tile[ly + SKY_R][threadIdx.x + SKY_R], c1 = tile[ly + 1 + SKY_R][threadIdx.x + SKY_R];
+    float wsum0 = 0.0f, prob0 = 0.0f, wsum1 = 0.0f, prob1 = 0.0f;
 #pragma unroll 1
     for (int i = -SKY_R; i <= SKY_R; ++i) {             // x offset (outer, as sky.cu:16)
+        float sp_prev = 0.f;
 #pragma unroll
-        for (int j = -SKY_R; j <= SKY_R; ++j) {         // y offset
-            const float4 t = tile[threadIdx.y + SKY_R + j][threadIdx.x + SKY_R + i];
-            const float b = t.x - c.x, g = t.y - c.y, r = t.z - c.z;
-            const float dis_color = sqrt(b * b + g * g + r * r);
-            const float w = exp(-spatial[i + SKY_R][j + SKY_R] - dis_color / sigma_color);
-            weight_sum += w;
-            prob += w * t.w;
+        for (int r = 0; r <= 2 * SKY_R + 1; ++r) {      // tile rows ly + r: y offset r - R for the upper pixel, r - 1 - R for the lower
+            const float4 t = tile[ly + r][threadIdx.x + SKY_R + i];
+            const float sp = spatial[i + SKY_R][r];
+            if (r <= 2 * SKY_R) {
+                const float b = t.x - c0.x, g = t.y - c0.y, q = t.z - c0.z;
+                const float dis_color = sqrt(b * b + g * g + q * q);
+                const float w = exp(-sp - dis_color / sigma_color);
+                wsum0 += w;
+                prob0 += w * t.w;
+            }
+            if (r >= 1) {
+                const float b = t.x - c1.x, g = t.y - c1.y, q = t.z - c1.z;
+                const float dis_color = sqrt(b * b + g * g + q * q);
+                const float w = exp(-sp_prev - dis_color / sigma_color);
+                wsum1 += w;
+                prob1 += w * t.w;
+            }
+            sp_prev = sp;
         }
     }
-    prob = prob / weight_sum;
+    prob0 = prob0 / wsum0;
     const size_t idx = (size_t)y * W + x;
-    result[idx] = prob > 0.6 ? 255 : 0;                 // sky.cu:34 (compared in double, as written there)
-    if (prob_out) prob_out[idx] = prob;
+    result[idx] = prob0 > 0.6 ? 255 : 0;                // sky.cu:34 (compared in double, as written there)
+    if (prob_out) prob_out[idx] = prob0;
+    if (y + 1 < H) {
+        prob1 = prob1 / wsum1;
+        result[idx + W] = prob1 > 0.6 ? 255 : 0;
+        if (prob_out) prob_out[idx + W] = prob1;
+    }
 }
 
 }  // namespace
@@ -151,7 +172,7 @@ int mpmvs_sky_mask_refine(int device, void* stream, const uint8_t* bgr, int widt
             T.mask_lo, mask_width, mask_height, T.mask, width, height, (double)mask_width / width, (double)mask_height / height);
     }
     SCK(cudaFuncSetAttribute(pm_sky_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKY_SMEM));
-    pm_sky_filter_kernel<<<dim3((width + SKY_BW - 1) / SKY_BW, (height + SKY_BH - 1) / SKY_BH), dim3(SKY_BW, SKY_BH), SKY_SMEM, st>>>(
+    pm_sky_filter_kernel<<<dim3((width + SKY_BW - 1) / SKY_BW, (height + SKY_PH - 1) / SKY_PH), dim3(SKY_BW, SKY_BH), SKY_SMEM, st>>>(
         T.bgr, T.mask, T.res, T.prob, width, height);
     SCK(cudaGetLastError());
     SCK(cudaEventRecord(T.e1, st));

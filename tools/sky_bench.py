@@ -27,9 +27,11 @@ try:
 except Exception:
     pass
 lds_peak = 128 * 148 * sm_mhz * 1e6            # bytes/s of shared-memory bandwidth
+xu_peak = 16 * 148 * sm_mhz * 1e6              # MUFU results/s (16 lanes/clk/SM)
 best = min(ms[1:]) if len(ms) > 1 else ms[0]
 out = {"size": f"{W}x{H}", "ms": [round(m, 3) for m in ms], "taps": taps, "gtaps_per_s": round(taps / best / 1e6, 1),
-       "smem_bytes_per_tap": 20, "smem_roof_frac": round(taps * 20 / (best * 1e-3) / lds_peak, 3),
+       "mufu_per_tap": 2, "xu_roof_frac": round(taps * 2 / (best * 1e-3) / xu_peak, 3),
+       "smem_bytes_per_tap": 10, "smem_roof_frac": round(taps * 10 / (best * 1e-3) / lds_peak, 3),
        "agreement_with_truth": round(float(((res > 0) == truth).mean()), 5)}
 if sky_oracle.ref_available():
     full = sky_oracle.resize_linear(lo, W, H)
