@@ -8,8 +8,8 @@
 //   pm_ncc_map_kernel<S>, pm_geom_map_kernel                 test hooks over pm_ncc / pm_geom_cost
 //   pm_export_depth_kernel   depth channel -> dense map (feeds the inter-GPU depth all-gather)
 //
-// Block = 32 x 8 threads, one thread per pixel. A sweep block owns a 32 x 16 pixel tile of one
-// checkerboard colour; the reference-image window of the tile (tile + 5*2^S halo) is staged once in
+// Block = 32 x PM_BH (4) threads, one thread per pixel. A sweep block owns the pixels of one checkerboard
+// colour in a 32 x 8 pixel tile; the reference-image window of the tile (tile + 5*2^S halo) is staged once in
 // shared memory through the texture unit (exact texel fetch, hardware clamp-to-edge at the borders),
 // the per-view constants sit next to it. Source samples go through the texture unit: they are
 // homography-warped scattered bilinear reads, which is what the unit is built for, and it keeps the
