@@ -55,10 +55,11 @@ def test_fails_loudly_without_gpu():
 
 def test_product_does_not_reference_oracle():
     """The product sources must not include, link or load anything under oracle/ (or the test emulation)."""
-    pkg = os.path.join(ROOT, "mp-mvs_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
-                text = open(os.path.join(dirpath, f), errors="ignore").read()
-                assert "pm_oracle" not in text and "oracle_py" not in text and "libmpmvs_ref" not in text, os.path.join(dirpath, f)
-                assert "pm_emul" not in text, os.path.join(dirpath, f)
+    words = ("pm_oracle", "oracle_py", "prior_oracle", "fusion_oracle", "sky_oracle", "libmpmvs_ref", "pm_emul")
+    for top in ("mp-mvs_b200", "tools", "include"):          # the package, the C ABI and the product-side tools
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
+                    text = open(os.path.join(dirpath, f), errors="ignore").read()
+                    for w in words:
+                        assert w not in text, (os.path.join(dirpath, f), w)

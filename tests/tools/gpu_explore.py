@@ -1,11 +1,11 @@
-"""Exploratory parity/timing report on a GPU box (prints, asserts nothing). Usage: python tools/gpu_explore.py [quick]"""
+"""Exploratory parity/timing report on a GPU box (prints, asserts nothing). Usage: python tests/tests/tools/gpu_explore.py [quick]"""
 import os
 import sys
 import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import PKG, gt_planes_cam, problem_arrays  # noqa: E402
 from cases import CASES, SEED, make_case, prior_planes, random_planes, src_depths, world_state_from_gt  # noqa: E402

@@ -2,8 +2,8 @@
 through the reference's own kernels (oracle/_ref) + restated host prior stage, identical seeds, Jacobi order on both sides.
 Reports accuracy at 2/5/10 cm against the synthetic ground truth for both, their agreement, and wall times.
 
-    python tools/scene_parity.py --scene dtu            # BASELINE config 2: 49 views 1600x1200, photometric + 2 geom
-    python tools/scene_parity.py --scene eth3d --planar 1 --geom-planar 1   # config 3, shipped default schedule
+    python tests/tests/tools/scene_parity.py --scene dtu            # BASELINE config 2: 49 views 1600x1200, photometric + 2 geom
+    python tests/tests/tools/scene_parity.py --scene eth3d --planar 1 --geom-planar 1   # config 3, shipped default schedule
 """
 import argparse
 import json
@@ -13,7 +13,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import PKG, problem_arrays  # noqa: E402
 import oracle_py  # noqa: E402

@@ -1,12 +1,12 @@
 """Sky-mask joint-bilateral upsampling at the ETH3D-shaped frame size: device time of pm_sky_filter_kernel against its
-shared-memory roof, next to the reference kernel when oracle/_ref is present.   python tools/sky_bench.py [W H reps]"""
+shared-memory roof, next to the reference kernel when oracle/_ref is present.   python tests/tests/tools/sky_bench.py [W H reps]"""
 import json
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
 import pkgload  # noqa: E402
 

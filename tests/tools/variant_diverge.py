@@ -1,6 +1,6 @@
 """Find where two builds of the library first diverge: step both through init + half-sweeps from identical states.
 
-usage: python tools/variant_diverge.py [variantA] [variantB] [case] [mode: photo|geom]
+usage: python tests/tests/tools/variant_diverge.py [variantA] [variantB] [case] [mode: photo|geom]
 Each build runs in a child process and saves the state after every half-sweep (always restarted from variant A's previous
 state, so a difference is local to one half-sweep); the parent reports the differing pixels.
 """
@@ -10,7 +10,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 OUT = "/tmp/mpmvs_diverge"      # states can be hundreds of MB: not under gpurun_out/
 
 

@@ -1,6 +1,6 @@
 """Check on the GPU that two builds of the library give bit-identical results (photometric, planar-prior and geometric runs).
 
-usage: python tools/variant_identity.py [variantA] [variantB] [case]    ("default" = the in-tree library)
+usage: python tests/tests/tools/variant_identity.py [variantA] [variantB] [case]    ("default" = the in-tree library)
 Each build runs in its own process (the library is chosen at import time by MPMVS_LIB_VARIANT) and prints one digest per
 run; the parent compares them.
 """
@@ -9,7 +9,7 @@ import os
 import subprocess
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
 def child(case_name: str) -> None:
