@@ -2,7 +2,7 @@
 // config.yaml -> pair.txt -> stage 1 (multi-scale photometric [+ planar prior]) -> geometric-consistency iterations
 // [+ planar prior] -> fusion -> MPMVS_model.ply, on the same dense-folder layout and with the same output files.
 //
-//   mpmvs_main [config.yaml] [--seed N] [--tex f32|u8] [--no-fusion] [--gpu-fusion] [--resident [--in-flight N] [--device D] [--gpus G]] [--profile]
+//   mpmvs_main [config.yaml] [--seed N] [--tex f32|u8] [--no-fusion] [--gpu-fusion] [--resident [--in-flight N] [--device D] [--gpus G]] [--profile] [--check-inputs DIR]
 //
 // Default: the reference's strictly sequential order (one ProcessProblem at a time, results exchanged in place).
 // --resident: every view uploaded once into a per-GPU image cache, one resident handle per reference image, depth maps
@@ -506,6 +506,50 @@ static void RunResident(const ConfigParams& config, std::vector<Scene>& Scenes, 
     cudaSetDevice(devices[0]);
 }
 
+// --check-inputs DIR: parse everything the run would parse (config.yaml, pair.txt, cameras, images incl. PatchMatchInit's
+// resize rule) WITHOUT touching the GPU, print it as JSON and write every (resized) image as DIR/%08d.dmb. The CPU test
+// suite compares this with the Python readers and with cv2.resize (tests/test_cpp_host.py).
+static void CheckInputs(const ConfigParams& c, std::vector<Scene>& Scenes, const std::string& dump_dir) {
+    auto arr = [](const float* v, int n) {
+        std::ostringstream o;
+        o << std::setprecision(9) << "[";
+        for (int i = 0; i < n; ++i) o << (i ? ", " : "") << v[i];
+        o << "]";
+        return o.str();
+    };
+    std::cout << "{\"config\": {\"input_folder\": \"" << c.input_folder << "\", \"output_folder\": \"" << c.output_folder << "\", \"geom_iterations\": "
+              << c.geom_iterations << ", \"planar_prior\": " << c.planar_prior << ", \"geomPlanarPrior\": " << c.geomPlanarPrior << ", \"sky_seg\": " << c.sky_seg
+              << ", \"use_dynamic_consistency\": " << c.use_dynamic_consistency << ", \"saveDmb\": " << c.saveDmb << ", \"saveProirDmb\": " << c.saveProirDmb
+              << ", \"saveCostDmb\": " << c.saveCostDmb << ", \"saveNormalDmb\": " << c.saveNormalDmb << ", \"MaxSourceImageNum\": " << c.MaxSourceImageNum
+              << ", \"MaxImageSize\": " << c.MaxImageSize << "},\n \"scenes\": [";
+    bool first = true;
+    for (size_t i = 0; i < Scenes.size(); ++i) {
+        Scene& sc = Scenes[i];
+        std::cout << (first ? "" : ",") << "\n  {\"index\": " << i << ", \"estimate\": " << sc.estimate << ", \"refID\": " << sc.refID << ", \"srcID\": [";
+        first = false;
+        for (size_t j = 0; j < sc.srcID.size(); ++j) std::cout << (j ? ", " : "") << sc.srcID[j];
+        std::cout << "]";
+        if (sc.estimate) {
+            Camera cam = ReadCamera(c.input_folder + "/cams/" + id8(sc.refID) + "_cam.txt");
+            GrayImage im;
+            if (!readGrayFile(c.input_folder + "/images/" + id8(sc.refID), im)) throw std::runtime_error("Can not read this image ! " + id8(sc.refID));
+            const int ow = im.width, oh = im.height;
+            if (im.width > c.MaxImageSize || im.height > c.MaxImageSize) {       // PatchMatch.cpp:893-925
+                const float factor = std::min((float)c.MaxImageSize / im.width, (float)c.MaxImageSize / im.height);
+                im = resizeLinear(im, (int)std::round(im.width * factor), (int)std::round(im.height * factor));
+                const float sx = im.width / (float)ow, sy = im.height / (float)oh;
+                cam.K[0] *= sx; cam.K[2] *= sx; cam.K[4] *= sy; cam.K[5] *= sy;
+            }
+            writeDmb(dump_dir + "/" + id8(sc.refID) + ".dmb", im.height, im.width, 1, im.px.data());
+            std::cout << ", \"K\": " << arr(cam.K, 9) << ", \"R\": " << arr(cam.R, 9) << ", \"t\": " << arr(cam.t, 3) << ", \"C\": " << arr(cam.C, 3)
+                      << ", \"depth_min\": " << std::setprecision(9) << cam.depth_min << ", \"depth_max\": " << cam.depth_max << ", \"width\": " << im.width
+                      << ", \"height\": " << im.height << ", \"orig_width\": " << ow << ", \"orig_height\": " << oh;
+        }
+        std::cout << "}";
+    }
+    std::cout << "\n ]}" << std::endl;
+}
+
 }  // namespace mpmvs
 
 int main(int argc, char* argv[]) {
@@ -514,6 +558,7 @@ int main(int argc, char* argv[]) {
     uint64_t seed = 0x2333;
     int tex = MPMVS_TEX_F32;
     bool fusion = true, gpu_fusion = false, profile = false, resident = false;
+    std::string check_dir;
     int in_flight = 8, device = 0, n_gpus = 1;   // host threads per GPU: the triangulation of the planar prior (up to 0.4 s per image) is host work
     for (int i = 1; i < argc; ++i) {
         if (!strcmp(argv[i], "--seed") && i + 1 < argc) seed = strtoull(argv[++i], nullptr, 0);
@@ -521,6 +566,7 @@ int main(int argc, char* argv[]) {
         else if (!strcmp(argv[i], "--no-fusion")) fusion = false;
         else if (!strcmp(argv[i], "--gpu-fusion")) gpu_fusion = true;
         else if (!strcmp(argv[i], "--profile")) profile = true;
+        else if (!strcmp(argv[i], "--check-inputs") && i + 1 < argc) check_dir = argv[++i];
         else if (!strcmp(argv[i], "--resident")) resident = true;
         else if (!strcmp(argv[i], "--in-flight") && i + 1 < argc) in_flight = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
@@ -529,6 +575,12 @@ int main(int argc, char* argv[]) {
     }
     try {
         ConfigParams config = readConfig(yaml);
+        if (!check_dir.empty()) {
+            std::vector<Scene> Scenes;
+            GenerateSampleList(config, Scenes);
+            CheckInputs(config, Scenes, check_dir);
+            return 0;
+        }
         std::cout << "Input data path:" << config.input_folder << "\nOutput data path:" << config.output_folder << std::endl;
         mkdir(config.output_folder.c_str(), 0777);
         std::vector<Scene> Scenes;

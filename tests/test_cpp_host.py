@@ -47,6 +47,58 @@ def test_main_reports_missing_inputs(tmp_path):
     assert r.returncode != 0 and "pair.txt" in r.stdout
 
 
+@pytest.mark.parametrize("max_size", [3200, 200])
+def test_host_parsers_match_the_python_readers(tmp_path, max_size):
+    """readConfig, GenerateSampleList, ReadCamera, the image loader with PatchMatchInit's resize rule and writeDmb of the
+    C++ host (`mpmvs_main --check-inputs`, no GPU involved) against io_formats and cv2.resize."""
+    import json
+
+    import cv2
+
+    build_main()
+    sc, root, yaml = write_scene(tmp_path, **{"Geometric consistency iterations": 1, "Planer prior": 0, "Sky segment": 1, "Save Cost Map": 1,
+                                              "Use dynamic_consistency to fuse": 0, "Max source images num": 3, "Max image size": max_size})
+    # a pair.txt with the quirks: a gap in the ids, a zero score, more sources than `Max source images num`, an image without sources
+    with open(os.path.join(root, "pair.txt"), "w") as f:
+        f.write("4\n0\n4 1 5.0 2 0.0 3 2.0 4 1.0\n1\n0\n2\n2 0 1.0 1 2.0\n5\n1 0 3.5\n")
+    dump = tmp_path / "dump"
+    dump.mkdir()
+    r = subprocess.run([MAIN, yaml, "--check-inputs", str(dump)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    got = json.loads(r.stdout)
+    cfg = PKG.io_formats.read_config(yaml)
+    c = got["config"]
+    assert c["input_folder"] == root and c["output_folder"] == root + "/MPMVS"          # utility.cpp:30
+    assert (c["geom_iterations"], c["planar_prior"], c["geomPlanarPrior"], c["sky_seg"], c["use_dynamic_consistency"]) == (1, 0, 1, 1, 0)
+    assert (c["saveDmb"], c["saveProirDmb"], c["saveCostDmb"], c["saveNormalDmb"]) == (0, 0, 1, 0)
+    assert c["MaxSourceImageNum"] == int(cfg["Max source images num"]) == 3 and c["MaxImageSize"] == max_size
+    want = PKG.io_formats.read_pairs(os.path.join(root, "pair.txt"), 3)
+    assert len(got["scenes"]) == len(want) == 6
+    for g, w in zip(got["scenes"], want):
+        assert bool(g["estimate"]) == w.estimate
+        if not w.estimate:
+            continue
+        assert g["refID"] == w.ref_id and g["srcID"] == w.src_ids
+        cam = PKG.io_formats.read_cam(os.path.join(root, "cams", f"{w.ref_id:08d}_cam.txt"))
+        img = cv2.imread(os.path.join(root, "images", f"{w.ref_id:08d}.pgm"), cv2.IMREAD_GRAYSCALE)
+        h, wd = img.shape
+        K = cam.K.astype(np.float32).copy()
+        ref_img = img.astype(np.float32)
+        if max(h, wd) > max_size:                                                        # PatchMatch.cpp:893-925
+            factor = min(np.float32(max_size) / np.float32(wd), np.float32(max_size) / np.float32(h))
+            nw, nh = int(round(float(np.float32(wd) * factor))), int(round(float(np.float32(h) * factor)))
+            ref_img = cv2.resize(ref_img, (nw, nh), interpolation=cv2.INTER_LINEAR)
+            sx, sy = np.float32(nw) / np.float32(wd), np.float32(nh) / np.float32(h)
+            K[0, 0] *= sx; K[0, 2] *= sx; K[1, 1] *= sy; K[1, 2] *= sy
+        assert (g["width"], g["height"], g["orig_width"], g["orig_height"]) == (ref_img.shape[1], ref_img.shape[0], wd, h)
+        np.testing.assert_allclose(np.array(g["K"]).reshape(3, 3), K, rtol=1e-6)
+        np.testing.assert_allclose(np.array(g["R"]).reshape(3, 3), cam.R, rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(g["t"], cam.t, rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(g["C"], cam.C, rtol=1e-5, atol=1e-6)
+        assert abs(g["depth_min"] - cam.depth_min) < 1e-6 and abs(g["depth_max"] - cam.depth_max) < 1e-6
+        np.testing.assert_allclose(PKG.io_formats.read_dmb(str(dump / f"{w.ref_id:08d}.dmb")), ref_img, atol=2e-3)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["default_schedule", "photometric_only_resized"])
 def test_main_end_to_end(tmp_path, mode):
