@@ -2,7 +2,7 @@
 // config.yaml -> pair.txt -> stage 1 (multi-scale photometric [+ planar prior]) -> geometric-consistency iterations
 // [+ planar prior] -> fusion -> MPMVS_model.ply, on the same dense-folder layout and with the same output files.
 //
-//   mpmvs_main [config.yaml] [--seed N] [--tex f32|u8] [--no-fusion] [--gpu-fusion] [--resident [--in-flight N] [--device D] [--gpus G]] [--profile] [--check-inputs DIR]
+//   mpmvs_main [config.yaml] [--seed N] [--tex f32|u8] [--no-fusion] [--gpu-fusion] [--resident [--in-flight N] [--device D] [--gpus G]] [--profile] [--check-inputs DIR] [--fusion-only]
 //
 // Default: the reference's strictly sequential order (one ProcessProblem at a time, results exchanged in place).
 // --resident: every view uploaded once into a per-GPU image cache, one resident handle per reference image, depth maps
@@ -557,7 +557,7 @@ int main(int argc, char* argv[]) {
     std::string yaml = "config/config.yaml";
     uint64_t seed = 0x2333;
     int tex = MPMVS_TEX_F32;
-    bool fusion = true, gpu_fusion = false, profile = false, resident = false;
+    bool fusion = true, gpu_fusion = false, profile = false, resident = false, fusion_only = false;
     std::string check_dir;
     int in_flight = 8, device = 0, n_gpus = 1;   // host threads per GPU: the triangulation of the planar prior (up to 0.4 s per image) is host work
     for (int i = 1; i < argc; ++i) {
@@ -566,6 +566,7 @@ int main(int argc, char* argv[]) {
         else if (!strcmp(argv[i], "--no-fusion")) fusion = false;
         else if (!strcmp(argv[i], "--gpu-fusion")) gpu_fusion = true;
         else if (!strcmp(argv[i], "--profile")) profile = true;
+        else if (!strcmp(argv[i], "--fusion-only")) fusion_only = true;     // fuse the .dmb files already in the result folders
         else if (!strcmp(argv[i], "--check-inputs") && i + 1 < argc) check_dir = argv[++i];
         else if (!strcmp(argv[i], "--resident")) resident = true;
         else if (!strcmp(argv[i], "--in-flight") && i + 1 < argc) in_flight = atoi(argv[++i]);
@@ -588,7 +589,9 @@ int main(int argc, char* argv[]) {
         const int num_img = (int)Scenes.size();
         std::cout << "There are " << num_img << " depthmaps need to be computed!\n" << std::endl;
         const auto t0 = std::chrono::steady_clock::now();
-        if (resident) {
+        if (fusion_only) {
+            // nothing to estimate: RunFusion below reads depths.dmb / normals.dmb of every image (host fusion needs no GPU)
+        } else if (resident) {
             mkdir(config.output_folder.c_str(), 0777);
             std::vector<int> devices;
             for (int g = 0; g < std::max(1, n_gpus); ++g) devices.push_back(device + g);
@@ -608,7 +611,7 @@ int main(int argc, char* argv[]) {
             const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
             printf("cost time is %.10f us\n", us);
         }
-        if (config.sky_seg) {                               // main.cpp:44-46
+        if (config.sky_seg && !fusion_only) {               // main.cpp:44-46
             const int n_sky = GenerateSkyRegionMask(Scenes, config);
             std::cout << "refined " << n_sky << " sky masks" << std::endl;
         }

@@ -95,3 +95,55 @@ def test_gpu_fusion_vs_sequential_host(tmp_path):
     f.destroy()
     print(f"GPU fusion {len(got)} points in {ms:.2f} ms; sequential host order {n_host} points")
     assert abs(len(got) - n_host) < 0.05 * n_host      # the orders differ only in which duplicate survives
+
+
+def test_host_fusion_matches_restatement_without_gpu(tmp_path):
+    """RunFusion restated in the C++ host (`mpmvs_main --fusion-only`: the reference's sequential order, no GPU involved)
+    against the numpy restatement (per-image snapshot order): same surface, point counts within the few percent by which the
+    two orders differ in which duplicate survives; the sky gate removes the gated pixels."""
+    from test_cpp_host import MAIN, build_main
+
+    import fusion_oracle
+
+    build_main()
+    sc, depths, normals, lists = noisy_scene(96, 72)
+    root = str(tmp_path / "dense")
+    PKG.synth.write_dense_folder(sc, root)                      # images/ (jpg + pgm), cams/, pair.txt
+    for i in range(sc.num_views):
+        d = io_formats.result_dir(root, i)
+        os.makedirs(d, exist_ok=True)
+        io_formats.write_dmb(os.path.join(d, "depths.dmb"), depths[i])
+        io_formats.write_dmb(os.path.join(d, "normals.dmb"), normals[i])
+    cams = io_formats.pack_cameras(sc.cams)
+
+    def run(**cfg):
+        yaml = str(tmp_path / "config.yaml")
+        io_formats.write_config(yaml, **dict({"Input-folder": root, "Output-folder": root, "Max source images num": 4}, **cfg))
+        r = subprocess.run([MAIN, yaml, "--fusion-only"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        n = int(r.stdout.split("store 3D points to ply file: ")[1].split(" points")[0])
+        with open(os.path.join(root, "MPMVS", "MPMVS_model.ply"), "rb") as fh:
+            raw = fh.read()
+        body = raw[raw.index(b"end_header\n") + len(b"end_header\n"):]
+        assert len(body) == n * 27                              # 6 floats + 3 colour bytes per vertex (PatchMatch.cpp:145-198)
+        pts = np.frombuffer(body, dtype=np.dtype([("p", "<f4", 3), ("n", "<f4", 3), ("c", "u1", 3)]))
+        return n, pts
+
+    for dyn in (1, 0):
+        n, pts = run(**{"Use dynamic_consistency to fuse": dyn})
+        want = fusion_oracle.fuse(cams, depths, normals, sc.images, lists, dynamic=bool(dyn))
+        assert abs(n - len(want)) < 0.08 * len(want), (n, len(want))      # measured 0.3 % (dynamic) and 5.8 % (fixed threshold)
+        key = lambda p: set(map(tuple, np.round(p * 1e3).astype(np.int64)))   # noqa: E731  (1 mm cells)
+        a, b = key(pts["p"]), key(want[:, :3])
+        assert len(a & b) > 0.75 * min(len(a), len(b))     # measured 0.83: the orders differ in which pixels of a surface patch get fused
+        assert np.isfinite(pts["p"]).all() and abs(float(np.linalg.norm(pts["n"], axis=1).mean()) - 1) < 0.05
+    # sky gate through the files the reference reads (skymask_refine.*): the top rows of every image are sky
+    n_open = n
+    for i in range(sc.num_views):
+        m = np.zeros(depths[i].shape, np.uint8)
+        m[:30] = 255
+        PKG.synth.write_pgm(os.path.join(io_formats.result_dir(root, i), "skymask_refine.pgm"), m)
+    n_gated, _ = run(**{"Use dynamic_consistency to fuse": 0, "Sky segment": 1})
+    sky = [np.where(np.arange(d.shape[0])[:, None] < 30, 255, 0).astype(np.uint8) * np.ones(d.shape, np.uint8) for d in depths]
+    want = fusion_oracle.fuse(cams, depths, normals, sc.images, lists, dynamic=False, sky=sky)
+    assert n_gated < n_open and abs(n_gated - len(want)) < 0.08 * len(want), (n_gated, n_open, len(want))
