@@ -57,3 +57,37 @@ def test_save_dmb_as_jpg_follows_the_yaml_keys(tmp_path):
     cfg.update({"Save Dmb as JPG": 1, "Save Cost Map": 1, "Save Normal Map": 1, "Save Prior Dmb as JPG": 1})
     assert previews.save_dmb_as_jpg(cfg, [3]) == 3          # no depths_prior.dmb was written: that preview is skipped
     assert sorted(f for f in os.listdir(folder) if f.endswith(".jpg")) == ["costs.jpg", "depths.jpg", "normals.jpg"]
+
+
+def test_cli_loaders_follow_the_reference_rules(tmp_path):
+    """run.py: PatchMatchInit's image rule (uint8 kept below `Max image size`, float resize above) and the sky files."""
+    import importlib.util
+
+    import cv2
+
+    spec = importlib.util.spec_from_file_location("mpmvs_run", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "mp-mvs_b200", "run.py"))
+    run = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(run)
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 255, (60, 90), dtype=np.uint8)
+    folder = str(tmp_path / "images")
+    os.makedirs(folder)
+    cv2.imwrite(os.path.join(folder, "00000007.pgm"), img)
+    a, sx, sy = run.load_image(folder, 7, 3200)
+    assert a.dtype == np.uint8 and (sx, sy) == (1.0, 1.0)
+    np.testing.assert_array_equal(a, img)
+    b, sx, sy = run.load_image(folder, 7, 45)                    # 90 x 60 -> 45 x 30 (PatchMatch.cpp:893-925)
+    assert b.dtype == np.float32 and b.shape == (30, 45) and abs(sx - 0.5) < 1e-6 and abs(sy - 0.5) < 1e-6
+    np.testing.assert_allclose(b, cv2.resize(img.astype(np.float32), (45, 30), interpolation=cv2.INTER_LINEAR))
+    with np.testing.assert_raises(FileNotFoundError):
+        run.load_image(folder, 8, 3200)
+    assert run.sky_image_size(90, 60, 3200) == (90, 60) and run.sky_image_size(90, 60, 45) == (45, 30)
+    # the sky gate RunFusion reads: skymask_refine.jpg brought to the depth map's size; absent file = no gate
+    out = str(tmp_path)
+    assert run.load_sky_mask(out, 7, (30, 45)) is None
+    d = io_formats.result_dir(out, 7)
+    os.makedirs(d)
+    m = np.zeros((60, 90), np.uint8); m[:20] = 255
+    cv2.imwrite(os.path.join(d, "skymask_refine.jpg"), m)
+    got = run.load_sky_mask(out, 7, (30, 45))
+    assert got.shape == (30, 45) and (got[:8] > 0).all() and (got[14:] > 0).mean() < 0.05
