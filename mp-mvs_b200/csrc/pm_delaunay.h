@@ -3,7 +3,7 @@
 // Replaces cv::Subdiv2D in PatchMatchCUDA::DelaunayTriangulation (/root/reference/src/PatchMatch.cpp:757-780), which
 // OpenCV-free builds cannot call. Vertices are pixel positions (one per 5x5 cell, GetTriangulateVertices :782-853), so
 // all predicates are evaluated exactly in 64/128-bit integers: no epsilons, no robustness fallbacks. Points are
-// inserted band by band in boustrophedon order (short walks whatever the caller's order) with Lawson flips. The triangulation of co-circular
+// inserted in the caller's order when that is a scan (as cv::Subdiv2D does), else band by band, with Lawson flips. The triangulation of co-circular
 // point sets is not unique (common on a pixel grid); like OpenCV's, the result is then ONE valid Delaunay triangulation.
 #ifndef MPMVS_PM_DELAUNAY_H
 #define MPMVS_PM_DELAUNAY_H
@@ -40,24 +40,38 @@ class Delaunay {
         t.n[0] = t.n[1] = t.n[2] = -1;
         tris_.push_back(t);
         last_ = 0;
-        // Insertion order: bands of rows walked boustrophedon, so that every point is located by a short walk from the
-        // previous one whatever order the caller used (a random order would make the walks O(sqrt n) each).
-        const int band = n > 0 ? (int)std::max(1.0, std::sqrt((double)width * height / n)) : 1;
-        const int n_bands = height / band + 1;
-        std::vector<int> start((size_t)n_bands + 1, 0), order((size_t)n);
-        for (int i = 0; i < n; ++i) ++start[xy[2 * i + 1] / band + 1];
-        for (int b = 0; b < n_bands; ++b) start[b + 1] += start[b];
-        {
-            std::vector<int> fill(start.begin(), start.end() - 1);
-            for (int i = 0; i < n; ++i) order[fill[xy[2 * i + 1] / band]++] = i;     // counting sort by band (stable)
-        }
-        for (int b = 0; b < n_bands; ++b) {                                          // then by x, alternating direction
-            const bool rev = b & 1;
-            std::sort(order.begin() + start[b], order.begin() + start[b + 1], [&](int p, int q) {
-                const int xp = xy[2 * p], xq = xy[2 * q];
-                if (xp != xq) return rev ? xp > xq : xp < xq;
-                return xy[2 * p + 1] != xy[2 * q + 1] ? xy[2 * p + 1] < xy[2 * q + 1] : p < q;
-            });
+        // Insertion order. Co-circular vertex quadruples are common on a pixel grid and which of their two diagonals
+        // survives depends on the order of insertion. cv::Subdiv2D inserts in the caller's order; GetTriangulateVertices
+        // (and mpmvs_pick_vertices) emit the cells row by row, so inserting in that order reproduces OpenCV's choice: every
+        // triangle built here is then one of OpenCV's (tests/test_prior_stage.py), against 99.3 % with a re-sorted order.
+        // A caller's order is kept when consecutive points are close to each other (a row-major scan jumps once per row);
+        // anything else (e.g. a shuffled set) would make every point-location walk O(sqrt n), so it is re-sorted into
+        // bands of rows walked boustrophedon.
+        std::vector<int> order((size_t)n);
+        double path = 0.0;
+        for (int i = 1; i < n; ++i) path += std::abs(xy[2 * i] - xy[2 * i - 2]) + std::abs(xy[2 * i + 1] - xy[2 * i - 1]);
+        const double spacing = n > 0 ? std::sqrt((double)width * height / n) : 1.0;
+        const bool keep_caller_order = n < 2 || path / (n - 1) <= 8.0 * spacing;
+        if (keep_caller_order) {
+            for (int i = 0; i < n; ++i) order[i] = i;
+        } else {
+            const int band = n > 0 ? (int)std::max(1.0, std::sqrt((double)width * height / n)) : 1;
+            const int n_bands = height / band + 1;
+            std::vector<int> start((size_t)n_bands + 1, 0);
+            for (int i = 0; i < n; ++i) ++start[xy[2 * i + 1] / band + 1];
+            for (int b = 0; b < n_bands; ++b) start[b + 1] += start[b];
+            {
+                std::vector<int> fill(start.begin(), start.end() - 1);
+                for (int i = 0; i < n; ++i) order[fill[xy[2 * i + 1] / band]++] = i;     // counting sort by band (stable)
+            }
+            for (int b = 0; b < n_bands; ++b) {                                          // then by x, alternating direction
+                const bool rev = b & 1;
+                std::sort(order.begin() + start[b], order.begin() + start[b + 1], [&](int p, int q) {
+                    const int xp = xy[2 * p], xq = xy[2 * q];
+                    if (xp != xq) return rev ? xp > xq : xp < xq;
+                    return xy[2 * p + 1] != xy[2 * q + 1] ? xy[2 * p + 1] < xy[2 * q + 1] : p < q;
+                });
+            }
         }
         for (int i = 0; i < n; ++i) insert(order[i]);
     }

@@ -68,6 +68,8 @@ def test_delaunay_against_opencv_and_empty_circle(kind):
     common = len(ours & cv)
     if kind in ("random", "cells", "tiny"):
         assert common >= 0.99 * len(cv) and len(ours) <= len(cv) + 2, (len(ours), len(cv), common)
+    if kind == "cells":                                      # a scan order is inserted as given, like cv::Subdiv2D: same tie-breaks
+        assert common == len(ours), (len(ours), len(cv), common)
     else:                                                    # degenerate sets: same count, same covered area
         assert abs(len(ours) - len(cv)) <= max(2, len(cv) // 50), (len(ours), len(cv))
 
