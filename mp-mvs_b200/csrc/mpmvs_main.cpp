@@ -588,6 +588,9 @@ int main(int argc, char* argv[]) {
         GenerateSampleList(config, Scenes);
         const int num_img = (int)Scenes.size();
         std::cout << "There are " << num_img << " depthmaps need to be computed!\n" << std::endl;
+        if (!resident && !fusion_only)
+            std::cout << "(reference order: one image at a time, results exchanged in place; --resident [--gpus G] keeps every view, state "
+                         "and depth map on the GPU(s) and is 2-3x faster)\n" << std::endl;
         const auto t0 = std::chrono::steady_clock::now();
         if (fusion_only) {
             // nothing to estimate: RunFusion below reads depths.dmb / normals.dmb of every image (host fusion needs no GPU)
