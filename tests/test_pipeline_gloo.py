@@ -149,3 +149,21 @@ def test_gpu_turn_is_fifo():
         pass
     with turn:
         pass
+
+
+def test_write_results_layout(tmp_path, oracle_cpu):
+    """DensePipeline.write_results: <out>/MPMVS/2333_%08d/{depths,normals,costs}.dmb written by background threads, holding
+    exactly what results() returns (the layout of PatchMatch.cpp:510-513,620-633)."""
+    entries, cams, images = make_inputs()
+    p = pipeline.DensePipeline(entries, cams, images, pipeline.PipelineConfig(geom_iterations=0, max_src=2, seed=5),
+                               engine_factory=lambda ids, imgs, packed: OracleEngine(ids, imgs, packed), torch_device=torch.device("cpu"))
+    p.run()
+    res = p.results()
+    p.write_results(str(tmp_path), writers=3)
+    p.destroy()
+    for ref, (planes, costs) in res.items():
+        d = io_formats.result_dir(str(tmp_path), ref)
+        assert d.endswith(f"MPMVS/2333_{ref:08d}")
+        np.testing.assert_array_equal(io_formats.read_dmb(os.path.join(d, "depths.dmb")), planes[..., 3])
+        np.testing.assert_array_equal(io_formats.read_dmb(os.path.join(d, "normals.dmb")), planes[..., :3])
+        np.testing.assert_array_equal(io_formats.read_dmb(os.path.join(d, "costs.dmb")), costs)
