@@ -28,7 +28,7 @@ ap.add_argument("--views", type=int, default=0)
 ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--tex", default="u8")
 ap.add_argument("--skip-reference", action="store_true")
-ap.add_argument("--in-flight", type=int, default=2)
+ap.add_argument("--in-flight", type=int, default=8)
 args = ap.parse_args()
 workers = min(32, os.cpu_count() or 1)
 t = time.time()

@@ -28,7 +28,7 @@ ap.add_argument("--size", default="1920x1080")
 ap.add_argument("--geom-iters", type=int, default=2)
 ap.add_argument("--planar", type=int, default=0)
 ap.add_argument("--geom-planar", type=int, default=0)
-ap.add_argument("--in-flight", type=int, default=2)
+ap.add_argument("--in-flight", type=int, default=8)
 ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out"))
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
