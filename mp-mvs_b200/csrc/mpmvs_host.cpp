@@ -77,23 +77,33 @@ void GenerateSampleList(const ConfigParams& config, std::vector<Scene>& Scenes) 
     if (!file.is_open()) throw std::runtime_error("can not open file in path: " + path);
     int num_images = 0;
     file >> num_images;
+    if (!file || num_images < 0) throw std::runtime_error("malformed pair.txt (image count): " + path);
     for (int i = 0; i < num_images; ++i) {
         Scene scene;
         scene.max_image_size = config.MaxImageSize;
         file >> scene.refID;
+        // ids index `Scenes` (PatchMatch.cpp:871-890 does Scenes[srcID[i]] unchecked): a truncated or out-of-order file
+        // must end in a message, not in an out-of-bounds access
+        if (!file || scene.refID < (int)Scenes.size()) throw std::runtime_error("malformed pair.txt (reference id of entry " + std::to_string(i) + "): " + path);
         scene.srcID.push_back(scene.refID);
         while (scene.refID > (int)Scenes.size()) Scenes.emplace_back();     // gaps in the ids: estimate == false
         int num_src = 0;
         file >> num_src;
+        if (!file || num_src < 0) throw std::runtime_error("malformed pair.txt (source count of image " + std::to_string(scene.refID) + "): " + path);
         for (int j = 0; j < num_src; ++j) {
-            int id; float score;
+            int id = -1; float score = 0.f;
             file >> id >> score;
+            if (!file || id < 0) throw std::runtime_error("malformed pair.txt (sources of image " + std::to_string(scene.refID) + "): " + path);
             if (score <= 0.0f) continue;
             if (j < config.MaxSourceImageNum) scene.srcID.push_back(id);
         }
         scene.estimate = num_src != 0;
         Scenes.push_back(std::move(scene));
     }
+    for (const Scene& sc : Scenes)
+        for (int id : sc.srcID)
+            if (id < 0 || id >= (int)Scenes.size())
+                throw std::runtime_error("pair.txt names image " + std::to_string(id) + ", which has no entry of its own: " + path);
 }
 
 Camera ReadCamera(const std::string& cam_path) {
@@ -110,6 +120,7 @@ Camera ReadCamera(const std::string& cam_path) {
     for (int i = 0; i < 3; ++i) cam.C[i] = -(cam.R[i] * cam.t[0] + cam.R[3 + i] * cam.t[1] + cam.R[6 + i] * cam.t[2]);   // C = -R^T t
     float interval, depth_num;
     file >> cam.depth_min >> interval >> depth_num >> cam.depth_max;
+    if (!file) throw std::runtime_error("malformed camera file: " + cam_path);
     return cam;
 }
 
@@ -118,7 +129,8 @@ bool readDmb(const std::string& path, int& h, int& w, int& nb, std::vector<float
     FILE* f = fopen(path.c_str(), "rb");
     if (!f) { std::cout << "Error opening file " << path << std::endl; return false; }
     int32_t hdr[4] = {-1, 0, 0, 0};
-    const bool ok = fread(hdr, sizeof(int32_t), 4, f) == 4 && hdr[0] == 1;
+    const bool ok = fread(hdr, sizeof(int32_t), 4, f) == 4 && hdr[0] == 1 && hdr[1] > 0 && hdr[2] > 0 && hdr[3] > 0 &&
+                    hdr[3] <= 4 && (int64_t)hdr[1] * hdr[2] <= (int64_t)1 << 28;     // a depth / normal / cost map, not garbage
     if (ok) {
         h = hdr[1]; w = hdr[2]; nb = hdr[3];
         data.resize((size_t)h * w * nb);
@@ -132,10 +144,11 @@ bool writeDmb(const std::string& path, int h, int w, int nb, const float* data) 
     FILE* f = fopen(path.c_str(), "wb");
     if (!f) { std::cout << "Error opening file " << path << std::endl; return false; }
     const int32_t hdr[4] = {1, h, w, nb};
-    fwrite(hdr, sizeof(int32_t), 4, f);
-    fwrite(data, sizeof(float), (size_t)h * w * nb, f);
-    fclose(f);
-    return true;
+    const size_t count = (size_t)h * w * nb;
+    bool ok = fwrite(hdr, sizeof(int32_t), 4, f) == 4 && fwrite(data, sizeof(float), count, f) == count;
+    ok = fclose(f) == 0 && ok;          // a full disk shows up here at the latest
+    if (!ok) std::cout << "Error writing file " << path << std::endl;
+    return ok;
 }
 
 // ---------------------------------------------------------------------------------------------- background writers
@@ -221,8 +234,10 @@ static bool readJpegLuma(const std::string& path, GrayImage& out) {
     static std::mutex decoder_mutex;               // one decoder state: callers on several threads take turns
     std::lock_guard<std::mutex> lock(decoder_mutex);
     if (!handle) {
-        if (nvjpegCreateSimple(&handle) != NVJPEG_STATUS_SUCCESS) return false;
-        if (nvjpegJpegStateCreate(handle, &state) != NVJPEG_STATUS_SUCCESS) return false;
+        nvjpegHandle_t hnd = nullptr;
+        if (nvjpegCreateSimple(&hnd) != NVJPEG_STATUS_SUCCESS) return false;
+        if (nvjpegJpegStateCreate(hnd, &state) != NVJPEG_STATUS_SUCCESS) { nvjpegDestroy(hnd); return false; }
+        handle = hnd;                              // published only together with its state
     }
     int comps = 0, ws[NVJPEG_MAX_COMPONENT], hs[NVJPEG_MAX_COMPONENT];
     nvjpegChromaSubsampling_t ss;
@@ -401,6 +416,8 @@ GrayImage resizeLinear(const GrayImage& src, int new_cols, int new_rows) {
 void PatchMatchCUDA::PatchMatchInit(std::vector<Scene>& Scenes, int ID) {
     images_.clear(); depths_.clear(); cameras_.clear();
     const std::vector<int>& srcID = Scenes[ID].srcID;
+    for (int id : srcID)
+        if (id < 0 || id >= (int)Scenes.size()) throw std::runtime_error("pair.txt names image " + std::to_string(id) + ", which has no entry of its own");
     ref_id_ = srcID[0];
     const std::string image_folder = input_folder_ + "/images", cam_folder = input_folder_ + "/cams";
     for (size_t i = 0; i < srcID.size(); ++i) {

@@ -232,7 +232,7 @@ int ensure_mirrors(mpmvs_problem* p) {
 
 // common tail of the three set_views flavours: cameras, depth range, per-view constants, state buffers
 int finish_views(mpmvs_problem* p, int n, const mpmvs_camera* cams) {
-    p->n = n;
+    p->n = 0;   // published at the end: after a failure every entry point that needs views answers MPMVS_E_ARG
     memcpy(p->cams, cams, sizeof(mpmvs_camera) * n);
     p->W = cams[0].width; p->H = cams[0].height;
     p->wh = (size_t)p->W * p->H;
@@ -248,6 +248,7 @@ int finish_views(mpmvs_problem* p, int n, const mpmvs_camera* cams) {
     int rc = alloc_state(p);
     if (rc) return rc;
     CK(cudaMemcpyAsync(p->dviews, p->hviews, sizeof(PmView) * (n - 1), cudaMemcpyHostToDevice, p->stream));
+    p->n = n;
     return MPMVS_OK;
 }
 
@@ -463,6 +464,7 @@ static int set_views_any(mpmvs_problem* p, int n, const void* const* imgs, bool 
     int rc = check_views_args(p, n, imgs, cams);
     if (rc) return rc;
     CK(cudaSetDevice(p->device));
+    p->n = 0;
     rc = private_cache(p, n, cams);
     if (rc) return rc;
     for (int i = 0; i < n; ++i) {
@@ -497,6 +499,7 @@ int mpmvs_set_views_cached(mpmvs_problem* p, mpmvs_image_cache* c, int n, const 
     if (rc) return rc;
     if (!c || c->device != p->device) return MPMVS_E_ARG;
     CK(cudaSetDevice(p->device));
+    p->n = 0;
     if (p->own_cache && p->cache) { cache_free(p->cache); delete p->cache; }
     p->cache = c;
     p->own_cache = false;
@@ -685,12 +688,12 @@ int mpmvs_get_depth_range(mpmvs_problem* p, float* depth_min, float* depth_max) 
 }
 
 int mpmvs_get_planes(mpmvs_problem* p, float* planes4_host) {
-    if (!p || !planes4_host || !p->h_planes) return MPMVS_E_ARG;
+    if (!p || !planes4_host || !p->h_planes || p->h_alloc < p->wh) return MPMVS_E_ARG;
     memcpy(planes4_host, p->h_planes, p->wh * sizeof(pm_f4));
     return MPMVS_OK;
 }
 int mpmvs_get_costs(mpmvs_problem* p, float* costs_host) {
-    if (!p || !costs_host || !p->h_costs) return MPMVS_E_ARG;
+    if (!p || !costs_host || !p->h_costs || p->h_alloc < p->wh) return MPMVS_E_ARG;
     memcpy(costs_host, p->h_costs, p->wh * sizeof(float));
     return MPMVS_OK;
 }
@@ -884,8 +887,9 @@ int mpmvs_pick_vertices(mpmvs_problem* p, int geom_variant, int* xy_out, int max
     return MPMVS_OK;
 }
 
-int mpmvs_prior_from_triangles(mpmvs_problem* p, const int* xy, int n_vertices, const int* tris, int n_tris, int* n_prior_pixels) {
-    if (!p || p->n < 2 || n_vertices < 0 || n_tris < 0 || (n_tris > 0 && (!xy || !tris))) return MPMVS_E_ARG;
+// upload + rasterisation + plane fit; indices are trusted (mpmvs_build_prior passes its own triangulation)
+static int prior_from_trusted_triangles(mpmvs_problem* p, const int* xy, int n_vertices, const int* tris, int n_tris,
+                                        int* n_prior_pixels) {
     CK(cudaSetDevice(p->device));
     // Grow with headroom: the counts differ a little from image to image and from pass to pass, and every cudaFree here
     // would wait for the whole device -- i.e. for the runs of the other images in flight -- before this image can go on.
@@ -912,6 +916,16 @@ int mpmvs_prior_from_triangles(mpmvs_problem* p, const int* xy, int n_vertices, 
     // sit here while it could already be enqueuing the next run or triangulating the next image
     if (n_prior_pixels) return mpmvs_get_prior_pixels(p, n_prior_pixels);
     return MPMVS_OK;
+}
+
+int mpmvs_prior_from_triangles(mpmvs_problem* p, const int* xy, int n_vertices, const int* tris, int n_tris, int* n_prior_pixels) {
+    if (!p || p->n < 2 || n_vertices < 0 || n_tris < 0 || (n_tris > 0 && (!xy || !tris))) return MPMVS_E_ARG;
+    // a caller's triangulation is read by the device as is: reject indices and positions that would leave the buffers
+    for (size_t i = 0; i < (size_t)3 * n_tris; ++i)
+        if (tris[i] < 0 || tris[i] >= n_vertices) return MPMVS_E_ARG;
+    for (int i = 0; i < n_vertices; ++i)
+        if (xy[2 * i] < 0 || xy[2 * i] >= p->W || xy[2 * i + 1] < 0 || xy[2 * i + 1] >= p->H) return MPMVS_E_ARG;
+    return prior_from_trusted_triangles(p, xy, n_vertices, tris, n_tris, n_prior_pixels);
 }
 
 int mpmvs_get_prior_pixels(mpmvs_problem* p, int* n_prior_pixels) {
@@ -942,7 +956,7 @@ int mpmvs_build_prior(mpmvs_problem* p, mpmvs_prior_stats* stats) {
     }
     const auto t2 = clk::now();
     // vertices and triangles are copied with cudaMemcpyAsync from pageable vectors: the runtime stages them before returning
-    rc = mpmvs_prior_from_triangles(p, xy.data(), nv, tris.data(), (int)(tris.size() / 3), nullptr);
+    rc = prior_from_trusted_triangles(p, xy.data(), nv, tris.data(), (int)(tris.size() / 3), nullptr);
     if (rc) return rc;
     const auto t3 = clk::now();
     if (stats) {

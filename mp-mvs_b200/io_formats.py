@@ -170,10 +170,19 @@ def read_pairs(path: str, max_src: int = 20) -> List[SceneEntry]:
     dropped, only the first ``max_src`` *listed positions* may be kept (j < max)."""
     toks = open(path).read().split()
     it = iter(toks)
+    try:
+        return _read_pairs(it, max_src)
+    except (StopIteration, ValueError) as e:       # same verdict as the C++ host (mpmvs_host.cpp, GenerateSampleList)
+        raise ValueError(f"malformed pair.txt: {path} ({e or 'truncated'})") from None
+
+
+def _read_pairs(it, max_src: int) -> List[SceneEntry]:
     n = int(next(it))
     scenes: List[SceneEntry] = []
     for _ in range(n):
         ref = int(next(it))
+        if ref < len(scenes):                      # scenes are indexed by image id: ids must ascend
+            raise ValueError(f"reference id {ref} out of order")
         sc = SceneEntry(ref_id=ref, src_ids=[ref])
         while ref > len(scenes):
             scenes.append(SceneEntry())
@@ -187,6 +196,10 @@ def read_pairs(path: str, max_src: int = 20) -> List[SceneEntry]:
                 sc.src_ids.append(sid)
         sc.estimate = ns != 0
         scenes.append(sc)
+    for sc in scenes:
+        for sid in sc.src_ids:
+            if not 0 <= sid < len(scenes):
+                raise ValueError(f"image {sid} has no entry of its own")
     return scenes
 
 

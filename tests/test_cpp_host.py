@@ -47,6 +47,38 @@ def test_main_reports_missing_inputs(tmp_path):
     assert r.returncode != 0 and "pair.txt" in r.stdout
 
 
+@pytest.mark.parametrize("pairs, message", [
+    ("3\n0\n1 1 1.0\n", "malformed pair.txt"),                       # truncated: three images announced, one present
+    ("2\n1\n1 0 1.0\n0\n1 1 1.0\n", "malformed pair.txt"),         # ids out of order: Scenes[id] would be another image
+    ("1\n0\n2 1 1.0 x\n", "malformed pair.txt"),                    # a source entry that is not a number
+    ("2\n0\n1 7 1.0\n1\n1 0 1.0\n", "no entry of its own"),        # a source id beyond the list (Scenes[7] in the reference)
+])
+def test_main_refuses_malformed_inputs(tmp_path, pairs, message):
+    """The reference indexes Scenes[srcID[i]] and reads pair.txt / cams unchecked (PatchMatch.cpp:67-143,871-890); the host
+    mirror must end such inputs with a message and a non-zero exit code, never with an out-of-bounds access."""
+    build_main()
+    sc, root, yaml = write_scene(tmp_path, 64, 48)
+    with open(os.path.join(root, "pair.txt"), "w") as f:
+        f.write(pairs)
+    dump = tmp_path / "dump"
+    dump.mkdir()
+    r = subprocess.run([MAIN, yaml, "--check-inputs", str(dump)], capture_output=True, text=True)
+    assert r.returncode == 1 and message in r.stdout, (r.returncode, r.stdout[-500:], r.stderr[-500:])
+
+
+def test_main_refuses_truncated_camera_and_dmb(tmp_path):
+    build_main()
+    sc, root, yaml = write_scene(tmp_path, 64, 48)
+    cam = os.path.join(root, "cams", "00000000_cam.txt")
+    text = open(cam).read().split()
+    with open(cam, "w") as f:
+        f.write(" ".join(text[:-3]))                                   # depth range cut off
+    dump = tmp_path / "dump"
+    dump.mkdir()
+    r = subprocess.run([MAIN, yaml, "--check-inputs", str(dump)], capture_output=True, text=True)
+    assert r.returncode == 1 and "malformed camera file" in r.stdout, (r.returncode, r.stdout[-500:])
+
+
 @pytest.mark.parametrize("max_size", [3200, 200])
 def test_host_parsers_match_the_python_readers(tmp_path, max_size):
     """readConfig, GenerateSampleList, ReadCamera, the image loader with PatchMatchInit's resize rule and writeDmb of the

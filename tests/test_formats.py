@@ -54,7 +54,7 @@ def test_pairs_rules(tmp_path):
     # GenerateSampleList, /root/reference/src/PatchMatch.cpp:67-109: score <= 0 dropped, first `max_src` kept, n_src == 0 skipped
     p = str(tmp_path / "pair.txt")
     with open(p, "w") as f:
-        f.write("3\n0\n3 1 5.0 2 0.0 3 2.0\n1\n0\n2\n2 0 1.0 1 2.0\n")
+        f.write("4\n0\n3 1 5.0 2 0.0 3 2.0\n1\n0\n2\n2 0 1.0 1 2.0\n3\n0\n")
     entries = io.read_pairs(p, max_src=1)
     by_ref = {e.ref_id: e for e in entries}
     assert by_ref[0].src_ids == [0, 1]            # srcID[0] is the reference itself (:84)
@@ -62,6 +62,20 @@ def test_pairs_rules(tmp_path):
     full = {e.ref_id: e for e in io.read_pairs(p, max_src=20)}
     assert full[0].src_ids == [0, 1, 3]           # score 0.0 dropped
     assert full[1].estimate is False and full[0].estimate is True
+
+
+@pytest.mark.parametrize("text", [
+    "3\n0\n1 1 1.0\n",                          # truncated
+    "2\n1\n1 0 1.0\n0\n1 1 1.0\n",            # ids out of order: scenes[id] would be another image
+    "1\n0\n2 1 1.0 x\n",                       # not a number
+    "2\n0\n1 7 1.0\n1\n1 0 1.0\n",            # a source without an entry (Scenes[7] in the reference, unchecked)
+])
+def test_pairs_malformed(tmp_path, text):
+    p = str(tmp_path / "pair.txt")
+    with open(p, "w") as f:
+        f.write(text)
+    with pytest.raises(ValueError):
+        io.read_pairs(p)
 
 
 def test_config_keys(tmp_path):

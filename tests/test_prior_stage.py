@@ -138,6 +138,10 @@ def test_gpu_prior_stage_vs_restatement(geom_variant):
     prior_w, mask_w, _, tris_px = prior_oracle.build_prior(planes, costs, K, dmin, dmax, geom)
     lut = {(int(x), int(y)): i for i, (x, y) in enumerate(verts)}
     tris_idx = np.array([[lut[(int(x), int(y))] for x, y in t] for t in tris_px], np.int32)
+    bad = tris_idx.copy()
+    bad[0, 0] = len(verts)                                                 # one past the last vertex: must be refused on the host
+    with pytest.raises(capi.MpmvsError):
+        pm.prior_from_triangles(verts, bad)
     n = pm.prior_from_triangles(verts, tris_idx)
     prior, mask = pm.get_prior()
     assert n == int((mask > 0).sum())
