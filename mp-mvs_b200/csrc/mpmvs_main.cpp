@@ -85,9 +85,10 @@ size_t RunFusion(const ConfigParams& config, std::vector<Scene>& Scenes) {
         const int id = Scenes[i].refID;
         cams[i] = ReadCamera(cam_folder + "/" + id8(id) + "_cam.txt");
         const std::string folder = config.input_folder + "/MPMVS/2333_" + id8(id);
-        int h, w, nb;
-        if (!readDmb(folder + "/depths.dmb", h, w, nb, depths[i]) || !readDmb(folder + "/normals.dmb", h, w, nb, normals[i]))
+        int h, w, nb, hn, wn, nbn;
+        if (!readDmb(folder + "/depths.dmb", h, w, nb, depths[i]) || !readDmb(folder + "/normals.dmb", hn, wn, nbn, normals[i]))
             throw std::runtime_error("fusion: missing results in " + folder);
+        if (nb != 1 || nbn != 3 || hn != h || wn != w) throw std::runtime_error("fusion: depths.dmb and normals.dmb do not belong together in " + folder);
         Scenes[i].depth.reset(); Scenes[i].normal.reset(); Scenes[i].cost.reset();     // the files are the interface from here on
         W[i] = w; H[i] = h;
         masks[i].assign((size_t)w * h, 0);
@@ -205,8 +206,10 @@ size_t RunFusionGPU(const ConfigParams& config, std::vector<Scene>& Scenes) {
             w = S.image.width; h = S.image.height;
             depth_px = S.depth->data(); normal_px = S.normal->data();
         } else {
-            if (!readDmb(folder + "/depths.dmb", h, w, nb, fdepth) || !readDmb(folder + "/normals.dmb", h, w, nb, fnormal))
+            int hn = 0, wn = 0, nbn = 0;
+            if (!readDmb(folder + "/depths.dmb", h, w, nb, fdepth) || !readDmb(folder + "/normals.dmb", hn, wn, nbn, fnormal))
                 throw std::runtime_error("fusion: missing results in " + folder);
+            if (nb != 1 || nbn != 3 || hn != h || wn != w) throw std::runtime_error("fusion: depths.dmb and normals.dmb do not belong together in " + folder);
             depth_px = fdepth.data(); normal_px = fnormal.data();
         }
         if (Scenes[i].image.empty() && !readGrayImage(image_folder, id, Scenes[i].image)) throw std::runtime_error("fusion: missing image " + id8(id));

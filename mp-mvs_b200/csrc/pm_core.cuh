@@ -39,7 +39,33 @@
 #ifndef PM_EARLY_OUT
 #define PM_EARLY_OUT 1   // stop scoring a refinement proposal once it can no longer be accepted (result-identical)
 #endif
+#ifndef PM_LITERAL_WARP
+// 1: warped tap coordinates in the reference's own operation order -- ComputeHomography per NCC call from the two
+// cameras (cu:228-279), ComputeCorrespondingPoint per tap on integer pixel positions (cu:281-288) -- instead of the
+// hoisted incremental form. Costs ~150 flop per NCC call and 3 FMA per tap; what it buys is source coordinates that are
+// bit-identical to the reference's, i.e. identical texture samples (a 1-ulp coordinate difference moves the unit's 8-bit
+// interpolation weights, which is most of the NCC difference to the reference). Experiment, off in
+// the shipped library; the expressions below are deliberately left to the compiler's own FMA contraction.
+#define PM_LITERAL_WARP 0
+#endif
+#ifndef PM_LITERAL_NCC
+// 1 (implies PM_LITERAL_WARP): the NCC sums as the reference forms them -- bilateral weight through sqrt / exp of the
+// run-time tap offsets (cu:318-323), per-row partial sums (cu:366-399), (w r) s products, variance and covariance in its
+// order, 1 - cov / sqrt(var var) (cu:400-413). On weak texture the variance is a difference of two numbers ~1e4 apart
+// from 1, so the last bit of every weight and the order of the additions are worth up to 1e-2 in cost: there the
+// difference to the reference comes from here, not from the coordinates (tests/tools/literal_ncc_check.py).
+// Still hoisted (bit-identical whether done once or per call): the reference-side sums and the centre pixel.
+#define PM_LITERAL_NCC 0
+#endif
+#if PM_LITERAL_NCC
+#undef PM_LITERAL_WARP
+#define PM_LITERAL_WARP 1
+#endif
 #define PM_PI_F 3.14159265358979323846f
+// The reference multiplies by M_PI, a double literal: `perturbation * M_PI` (cu:671), `3 * perturbation * M_PI` (cu:559)
+// and `M_PI * (5.0f / 180.0f)` (cu:651,929) are double products narrowed to float -- 0.06283185 and 0.08726646, one
+// ulp below the float products 0.06283186 and 0.08726647. Compile-time constants either way.
+#define PM_PI_D 3.14159265358979323846
 
 struct alignas(16) pm_f4 { float x, y, z, w; };
 
@@ -56,6 +82,9 @@ struct PmView {
     int dpitch;   // in floats
     int layer;    // layer of this view in the resident layered image texture
     const float* depth;        // source depth map (geom pass), linear device memory
+#if PM_LITERAL_WARP
+    float sK[9], sR[9], st[3], sC[3];   // the source camera as the reference holds it (struct Camera, PatchMatch.h:35-46)
+#endif
 };
 
 // Reference-camera constants and run flags.
@@ -74,6 +103,11 @@ struct PmFrame {
     int soft_clamp;            // 1 when the views differ in size: clamp-to-edge is then done on the coordinates
     unsigned long long tex;    // cudaTextureObject_t of the layered image array (one handle, warp-uniform:
                                // a per-view handle makes the compiler serialise every fetch per unique handle)
+#if PM_LITERAL_WARP
+    float K[9], t[3], C[3];    // the rest of the reference camera (R is above): ComputeHomography, BackProjectPoint2W, ProjectPoint
+    int one;                   // 1, as a run-time value: keeps the tap offsets of the literal weight out of constant folding
+    float sigma_spatial, sigma_color;
+#endif
 };
 
 // Device-resident per-pixel state (SoA).
@@ -154,7 +188,13 @@ PM_HD float pm_dot3(const pm_f4& a, const pm_f4& b) { return a.x * b.x + a.y * b
 
 // ComputeDepthfromPlaneHypothesis, cu:84-87
 PM_HD float pm_depth_from_plane(const PmFrame& F, const pm_f4& pl, int x, int y) {
+#if PM_LITERAL_NCC
+    // K[0] / K[4] is formed on the device by the reference (an approximate division under --use_fast_math, not
+    // necessarily 1 when the two are equal), not on the host
+    return -pl.w * F.fx / ((x - F.cx) * pl.x + (F.fx / F.fy) * (y - F.cy) * pl.y + F.fx * pl.z);
+#else
     return -pl.w * F.fx / ((x - F.cx) * pl.x + F.fx_over_fy * (y - F.cy) * pl.y + F.fx * pl.z);
+#endif
 }
 // GetPlane2Origin, cu:163-176
 PM_HD float pm_plane_distance(const PmFrame& F, int x, int y, float depth, const pm_f4& n) {
@@ -235,11 +275,51 @@ struct PmRefStats {
     float var_r;     // weighted variance of the reference patch
 };
 
+#if PM_LITERAL_NCC
+// ComputeBilateralWeight, cu:318-323. The offsets arrive as run-time values (the reference's loop counters are), so the
+// square root is the device's approximate one under --use_fast_math there and here, not a compile-time constant.
+PM_HD float pm_weight_literal(float x_dist, float y_dist, float pix, float center_pix, float sigma_spatial, float sigma_color) {
+    const float spatial_dist = sqrtf(x_dist * x_dist + y_dist * y_dist);
+    const float color_dist = fabsf(pix - center_pix);
+    return expf(-spatial_dist / (2.0f * sigma_spatial * sigma_spatial) - color_dist / (2.0f * sigma_color * sigma_color));
+}
+#endif
+
 template <int SCALE, class Ctx, int TAPS = 6>
 PM_HD PmRefStats pm_ref_stats(const Ctx& c, const PmFrame& F) {
     constexpr int HS = 1 << SCALE;  // step/2: taps at (2a-5)*HS
     PmRefStats st;
     st.r0 = c.ref(0, 0);
+#if PM_LITERAL_NCC
+    {   // the reference-side half of cu:355-405: rows of the window are summed on their own, then added up
+        // run-time loop bounds, not unrolled: the reference's loops are (cu:340-346,365,373), and the compiler's choice of
+        // which products to fuse into FMAs follows the loop structure (unrolled taps get their spatial term hoisted and
+        // the colour term fused; the reference's SASS rounds the colour term and fuses the spatial one)
+        const int step = 2 * HS * F.one, radius = (TAPS - 1) * step / 2;
+        float sum_ref = 0.0f, sum_ref_ref = 0.0f, weight_sum = 0.0f;
+#pragma unroll 1
+        for (int i = -radius; i < radius + 1; i += step) {
+            float row_ref = 0.0f, row_ref_ref = 0.0f, row_weight = 0.0f;
+#pragma unroll 1
+            for (int j = -radius; j < radius + 1; j += step) {
+                const float r = c.ref(i, j);
+                const float w = pm_weight_literal(i, j, r, st.r0, F.sigma_spatial, F.sigma_color);
+                row_ref += w * r;
+                row_ref_ref += w * r * r;
+                row_weight += w;
+            }
+            sum_ref += row_ref;
+            sum_ref_ref += row_ref_ref;
+            weight_sum += row_weight;
+        }
+        st.inv_sw = 1.0f / weight_sum;
+        sum_ref *= st.inv_sw;
+        sum_ref_ref *= st.inv_sw;
+        st.mean_r = sum_ref;
+        st.var_r = sum_ref_ref - sum_ref * sum_ref;
+        return st;
+    }
+#endif
     float sw = 0.f, swr = 0.f, swrr = 0.f;
 #pragma unroll
     for (int a = 0; a < TAPS; ++a) {
@@ -260,10 +340,18 @@ PM_HD PmRefStats pm_ref_stats(const Ctx& c, const PmFrame& F) {
 }
 
 // Per-hypothesis part of the homography: m = K_r^-T n / d, q0 = m . (x, y, 1)  (= -1/z at the pixel).
-struct PmHyp { float mx, my, q0; };
+struct PmHyp {
+    float mx, my, q0;
+#if PM_LITERAL_WARP
+    pm_f4 pl;
+#endif
+};
 PM_HD PmHyp pm_hyp(const PmFrame& F, const pm_f4& pl, int x, int y) {
     const float id = 1.0f / pl.w;
     PmHyp h;
+#if PM_LITERAL_WARP
+    h.pl = pl;
+#endif
     h.mx = pl.x * F.ifx * id;
     h.my = pl.y * F.ify * id;
     const float mz = (pl.z - pl.x * F.cx * F.ifx - pl.y * F.cy * F.ify) * id;
@@ -271,12 +359,123 @@ PM_HD PmHyp pm_hyp(const PmFrame& F, const pm_f4& pl, int x, int y) {
     return h;
 }
 
+#if PM_LITERAL_WARP
+// ComputeHomography, cu:228-279, operation by operation (relative pose, plane term, K_r^-1 with zero skew, the part of
+// K_s it uses); plain expressions, so nvcc contracts them the way it contracts the reference's.
+PM_HD void pm_homography_literal(const PmFrame& F, const PmView& V, const pm_f4& pl, float* H) {
+    float Rrel[9], trel[3], tmp[9];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+            Rrel[3 * a + b] = V.sR[3 * a] * F.R[3 * b] + V.sR[3 * a + 1] * F.R[3 * b + 1] + V.sR[3 * a + 2] * F.R[3 * b + 2];
+    }
+    const float c0 = F.C[0] - V.sC[0], c1 = F.C[1] - V.sC[1], c2 = F.C[2] - V.sC[2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) trel[a] = V.sR[3 * a] * c0 + V.sR[3 * a + 1] * c1 + V.sR[3 * a + 2] * c2;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        H[3 * a] = Rrel[3 * a] - trel[a] * pl.x / pl.w;
+        H[3 * a + 1] = Rrel[3 * a + 1] - trel[a] * pl.y / pl.w;
+        H[3 * a + 2] = Rrel[3 * a + 2] - trel[a] * pl.z / pl.w;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        tmp[3 * a] = H[3 * a] / F.fx;
+        tmp[3 * a + 1] = H[3 * a + 1] / F.fy;
+        tmp[3 * a + 2] = -H[3 * a] * F.cx / F.fx - H[3 * a + 1] * F.cy / F.fy + H[3 * a + 2];
+    }
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        H[b] = V.sK[0] * tmp[b] + V.sK[2] * tmp[6 + b];
+        H[3 + b] = V.sK[4] * tmp[3 + b] + V.sK[5] * tmp[6 + b];
+        H[6 + b] = V.sK[8] * tmp[6 + b];
+    }
+}
+// ComputeCorrespondingPoint, cu:281-288, on an integer pixel position
+PM_HD void pm_warp_literal(const float* H, int px, int py, float& ox, float& oy) {
+    const float X = H[0] * px + H[1] * py + H[2];
+    const float Y = H[3] * px + H[4] * py + H[5];
+    const float Z = H[6] * px + H[7] * py + H[8];
+    ox = X / Z;
+    oy = Y / Z;
+}
+#endif
+
 // ComputeBilateralNCC, cu:325-414: cost of hypothesis `hyp` at pixel (x,y) against source view v.
 template <int SCALE, class Ctx, int TAPS = 6>
 PM_HD float pm_ncc(const Ctx& c, const PmFrame& F, const PmRefStats& st, int v, const PmHyp& hyp, int x, int y,
                    uint32_t& nexec) {
     constexpr int HS = 1 << SCALE;
     const PmView& V = c.view(v);
+#if PM_LITERAL_WARP
+    float Hm[9];
+    pm_homography_literal(F, V, hyp.pl, Hm);
+    float pcx, pcy;
+    pm_warp_literal(Hm, x, y, pcx, pcy);
+    if (pcx >= V.w || pcx < 0.0f || pcy >= V.h || pcy < 0.0f) return 2.0f;  // cu:351-353
+    if (st.var_r < 1e-5f) return 2.0f;                                     // cu:407 (hypothesis-invariant)
+    ++nexec;
+#if PM_LITERAL_NCC
+    // source-side half of cu:355-413
+    const int step = 2 * HS * F.one, radius = (TAPS - 1) * step / 2;     // run-time bounds: see pm_ref_stats
+    float sum_src = 0.0f, sum_src_src = 0.0f, sum_ref_src = 0.0f;
+#pragma unroll 1
+    for (int i = -radius; i < radius + 1; i += step) {
+        float row_src = 0.0f, row_src_src = 0.0f, row_ref_src = 0.0f;
+#pragma unroll 1
+        for (int j = -radius; j < radius + 1; j += step) {
+            const float r = c.ref(i, j);
+            float sx, sy;
+            pm_warp_literal(Hm, x + i, y + j, sx, sy);
+            const float s = c.src(v, sx + 0.5f, sy + 0.5f);
+            const float w = pm_weight_literal(i, j, r, st.r0, F.sigma_spatial, F.sigma_color);
+            row_src += w * s;
+            row_src_src += w * s * s;
+            row_ref_src += w * r * s;
+        }
+        sum_src += row_src;
+        sum_src_src += row_src_src;
+        sum_ref_src += row_ref_src;
+    }
+    sum_src *= st.inv_sw;
+    sum_src_src *= st.inv_sw;
+    const float var_src = sum_src_src - sum_src * sum_src;
+#if defined(__CUDA_ARCH__)
+    // The reference scales sum_ref_src before its variance test, so its compiled covariance is FFMA(-mean_r, mean_s,
+    // round(sum_ref_src * inv)) (SASS of oracle/_ref, RefNccMap / BlackPixelUpdate); left to itself the compiler fuses the
+    // other product here because the scaling can sink below the early return. Pinned explicitly.
+    sum_ref_src = __fmul_rn(sum_ref_src, st.inv_sw);
+    if (var_src < 1e-5f) return 2.0f;
+    const float covar_src_ref = __fmaf_rn(-st.mean_r, sum_src, sum_ref_src);
+#else
+    sum_ref_src *= st.inv_sw;
+    if (var_src < 1e-5f) return 2.0f;
+    const float covar_src_ref = sum_ref_src - st.mean_r * sum_src;
+#endif
+    const float var_ref_src = sqrtf(st.var_r * var_src);
+    return fmaxf(0.0f, fminf(2.0f, 1.0f - covar_src_ref / var_ref_src));
+#else
+    float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int a = 0; a < TAPS; ++a) {
+        const int i = (2 * a - (TAPS - 1)) * HS;
+#pragma unroll
+        for (int b = 0; b < TAPS; ++b) {
+            const int j = (2 * b - (TAPS - 1)) * HS;
+            float sx, sy;
+            pm_warp_literal(Hm, x + i, y + j, sx, sy);
+            const float s = c.src(v, sx + 0.5f, sy + 0.5f);
+            const float r = c.ref(i, j);
+            const float w = pm_ex2(fmaf(fabsf(r - st.r0), -F.col_k, (HS * pm_tap_dist_n<TAPS>(2 * a - (TAPS - 1), 2 * b - (TAPS - 1))) * F.spat_k));
+            const float ws = w * s;
+            s1 += ws;
+            s2 = fmaf(ws, s, s2);
+            s3 = fmaf(ws, r, s3);
+        }
+    }
+#endif
+#else
     const float fxp = (float)x, fyp = (float)y;
     // warped centre  P0 = A (x,y,1) + b q0 ; tap steps  U = H e_x, Vv = H e_y
     const float X0 = fmaf(V.b[0], hyp.q0, fmaf(V.A[0], fxp, fmaf(V.A[1], fyp, V.A[2])));
@@ -310,17 +509,58 @@ PM_HD float pm_ncc(const Ctx& c, const PmFrame& F, const PmRefStats& st, int v, 
             s3 = fmaf(ws, r, s3);
         }
     }
+#endif
+#if !PM_LITERAL_NCC
     const float mean_s = s1 * st.inv_sw;
     const float var_s = s2 * st.inv_sw - mean_s * mean_s;
     if (var_s < 1e-5f) return 2.0f;
     const float cov = s3 * st.inv_sw - st.mean_r * mean_s;
     return fmaxf(0.0f, fminf(2.0f, 1.0f - cov * pm_rsqrt(st.var_r * var_s)));
+#endif
 }
 
 // ComputeGeomConsistencyCost, cu:617-640, with the four camera transforms pre-multiplied per view.
+#if PM_LITERAL_NCC
+// BackProjectPoint2W, cu:582-603, and ProjectPoint, cu:605-615, on a camera given as (K, R, t, C)
+PM_HD void pm_backproject_literal(float x, float y, float depth, const float* K, const float* R, const float* C, float* X) {
+    const float px = depth * (x - K[2]) / K[0];
+    const float py = depth * (y - K[5]) / K[4];
+    const float pz = depth;
+    const float tx = R[0] * px + R[3] * py + R[6] * pz;
+    const float ty = R[1] * px + R[4] * py + R[7] * pz;
+    const float tz = R[2] * px + R[5] * py + R[8] * pz;
+    X[0] = tx + C[0];
+    X[1] = ty + C[1];
+    X[2] = tz + C[2];
+}
+PM_HD void pm_project_literal(const float* X, const float* K, const float* R, const float* t, float& u, float& v) {
+    const float tx = R[0] * X[0] + R[1] * X[1] + R[2] * X[2] + t[0];
+    const float ty = R[3] * X[0] + R[4] * X[1] + R[5] * X[2] + t[1];
+    const float tz = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + t[2];
+    const float depth = K[6] * tx + K[7] * ty + K[8] * tz;
+    u = (K[0] * tx + K[1] * ty + K[2] * tz) / depth;
+    v = (K[3] * tx + K[4] * ty + K[5] * tz) / depth;
+}
+#endif
+
 template <class Ctx>
 PM_HD float pm_geom_cost(const Ctx& c, const PmFrame& F, int v, const pm_f4& pl, int x, int y) {
     const PmView& V = c.view(v);
+#if PM_LITERAL_NCC
+    {   // cu:617-640 through the two cameras, not through the pre-multiplied per-view transforms
+        const float depth = pm_depth_from_plane(F, pl, x, y);
+        float P3[3], sx, sy;
+        pm_backproject_literal((float)x, (float)y, depth, F.K, F.R, F.C, P3);
+        pm_project_literal(P3, V.sK, V.sR, V.st, sx, sy);
+        const float sd = c.src_depth(v, pm_f2i(sx), pm_f2i(sy));
+        if (sd == 0.0f) return 3.0f;
+        float Q3[3], bx, by;
+        pm_backproject_literal(sx, sy, sd, V.sK, V.sR, V.sC, Q3);
+        pm_project_literal(Q3, F.K, F.R, F.t, bx, by);
+        const float diff_col = x - bx, diff_row = y - by;
+        return fminf(3.0f, sqrtf(diff_col * diff_col + diff_row * diff_row));
+    }
+#endif
     const float z = pm_depth_from_plane(F, pl, x, y);
     const float fxp = (float)x, fyp = (float)y;
     const float hx = fmaf(z, fmaf(V.Mf[0], fxp, fmaf(V.Mf[1], fyp, V.Mf[2])), V.vf[0]);
@@ -444,7 +684,7 @@ PM_HD void pm_sweep_pixel(const Ctx& c, const PmFrame& F, const PmState& S, int 
 
     const float depth_sigma = (F.depth_max - F.depth_min) / 64.0f;
     const float two_ds2 = 2 * depth_sigma * depth_sigma;
-    const float angle_sigma = PM_PI_F * (5.0f / 180.0f);
+    const float angle_sigma = (float)(PM_PI_D * (5.0f / 180.0f));
     const float two_as2 = 2 * angle_sigma * angle_sigma;
 
     const pm_f4 cur = S.planes[idx];
@@ -595,7 +835,7 @@ PM_HD void pm_sweep_pixel(const Ctx& c, const PmFrame& F, const PmState& S, int 
             // QUIRK cu:668-670: `while (d < min && d > max)` can never hold, so exactly one draw
             const float dlo = (1 - perturbation) * depth_now, dhi = (1 + perturbation) * depth_now;
             depth_pert = pm_uniform(rs) * (dhi - dlo) + dlo;
-            pert_n = pm_perturbed_normal(F, x, y, plane_now, rs, perturbation * PM_PI_F);
+            pert_n = pm_perturbed_normal(F, x, y, plane_now, rs, (float)(perturbation * PM_PI_D));
             base_n = plane_now;
             depth_base = depth_now;
         }
@@ -701,7 +941,7 @@ PM_HD void pm_init_pixel(const Ctx& c, const PmFrame& F, const PmState& S, int x
         const pm_f4 pp = S.prior[idx];
         const float lo = (1 - 3 * perturbation) * pp.w, hi = (1 + 3 * perturbation) * pp.w;
         const float dp = pm_uniform(rs) * (hi - lo) + lo;
-        pl = pm_perturbed_normal(F, x, y, pp, rs, 3 * perturbation * PM_PI_F);
+        pl = pm_perturbed_normal(F, x, y, pp, rs, (float)(3 * perturbation * PM_PI_D));
         pl.w = dp;
     } else {
         // stored (world normal, depth) -> (camera normal, plane distance)

@@ -74,6 +74,10 @@ inline void pm_build_view_consts(const mpmvs_camera& rc, const mpmvs_camera& sc,
     V.dh = sc.height;
     V.dpitch = sc.width;
     V.depth = nullptr;
+#if PM_LITERAL_WARP
+    for (int i = 0; i < 9; ++i) { V.sK[i] = sc.K[i]; V.sR[i] = sc.R[i]; }
+    for (int i = 0; i < 3; ++i) { V.st[i] = sc.t[i]; V.sC[i] = sc.C[i]; }
+#endif
 }
 
 
@@ -90,6 +94,12 @@ inline PmFrame pm_make_frame(const mpmvs_camera& c, int n, float depth_min, floa
     F.col_k = (float)(log2e / (2.0 * sigma_color * sigma_color));
     F.W = c.width; F.H = c.height; F.nsrc = n - 1; F.top_k = top_k;
     F.geom = geom ? 1 : 0; F.planar = planar ? 1 : 0;
+#if PM_LITERAL_WARP
+    for (int i = 0; i < 9; ++i) F.K[i] = c.K[i];
+    for (int i = 0; i < 3; ++i) { F.t[i] = c.t[i]; F.C[i] = c.C[i]; }
+    F.one = 1;
+    F.sigma_spatial = sigma_spatial; F.sigma_color = sigma_color;
+#endif
     return F;
 }
 #endif

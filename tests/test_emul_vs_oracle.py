@@ -169,3 +169,47 @@ def test_restructurings_are_bit_identical(libs):
         for a, b in zip(results["_plain"], results[tag]):
             for x, y in zip(a, b):
                 np.testing.assert_array_equal(x, y)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_literal_variant_is_bit_identical_to_the_oracle(libs, name):
+    """-DPM_LITERAL_NCC=1 (pm_core.cuh): homography, tap coordinates, bilateral weights, NCC sums and the geometric cost in
+    the reference's own operation order. Instantiated on the host, the product's per-pixel templates must then reproduce
+    the literal restatement (oracle/pm_oracle.c) BIT FOR BIT over whole runs in all three modes -- every plane, cost,
+    geometric cost and RNG draw. This pins the control flow and every piece of arithmetic outside the NCC of the shipped
+    build too (the two builds differ only inside `#if PM_LITERAL_*`)."""
+    from conftest import build_emul as be
+
+    libs.LIBS["emul_literal"] = (be("_literal", ["-DPM_LITERAL_NCC=1"]), "emu_")
+    c = make_case(name)
+    o = libs.Oracle("cpu").set_problem(c["images"], c["cams"])
+    e = libs.Oracle("emul_literal").set_problem(c["images"], c["cams"])
+    pl = random_planes(c)
+    for s in (0, 1, 2):
+        np.testing.assert_array_equal(o.ncc_map(pl, s), e.ncc_map(pl, s))
+    for x in (o, e):
+        x.set_geom_consistency_params(False, False)
+        x.run(SEED)
+    for a, b in zip(o.result(), e.result()):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(o.get_state()["rng"], e.get_state()["rng"])
+    for x in (o, e):
+        x.set_planar_prior_params()
+        x.set_geom_consistency_params(False, True)
+        x.set_prior(*prior_planes(c))
+        x.run(SEED + 1)
+    for a, b in zip(o.result(), e.result()):
+        np.testing.assert_array_equal(a, b)
+    o.destroy(); e.destroy()
+    o = libs.Oracle("cpu").set_problem(c["images"], c["cams"])
+    e = libs.Oracle("emul_literal").set_problem(c["images"], c["cams"])
+    for x in (o, e):
+        x.set_geom_consistency_params(True, False)
+        x.set_src_depths(src_depths(c, 0.002))
+        x.set_state(*world_state_from_gt(c))
+    np.testing.assert_array_equal(o.geom_map(pl), e.geom_map(pl))
+    for x in (o, e):
+        x.run(SEED + 2)
+    for a, b in zip(o.result(geom=True), e.result(geom=True)):
+        np.testing.assert_array_equal(a, b)
+    o.destroy(); e.destroy()

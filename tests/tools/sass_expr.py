@@ -1,0 +1,157 @@
+"""Compare, symbolically, the floating-point expressions two SASS listings compute (tests/tools, no GPU needed).
+
+Why: the literal variant (-DPM_LITERAL_NCC=1, pm_core.cuh) is meant to be BIT-identical to the reference's compiled kernels,
+and under --use_fast_math that depends on which multiplies the compiler fuses into FMAs -- visible only in the SASS. This
+tool executes a straight-line stretch of SASS symbolically (FMUL / FFMA / FADD / MUFU / I2F; loads are leaves), builds the
+expression tree of chosen registers and prints it in a canonical form (commutative operands sorted, leaves anonymous), so
+that the reference's build (cuobjdump -sass oracle/_ref/libmpmvs_ref.so) and ours can be diffed modulo register
+allocation and scheduling.
+
+    python tests/tools/sass_expr.py ref.sass  RefNccMap        # prints the trees feeding the first source TEX in a loop
+    python tests/tools/sass_expr.py ours.sass pm_ncc_map_kernelILi0ELb0ELb0
+"""
+import re
+import sys
+
+FP = {"FMUL": 2, "FADD": 2, "FFMA": 3}
+
+
+def function_body(path, name):
+    out, on = [], False
+    for line in open(path):
+        if "Function :" in line:
+            if on:
+                break
+            on = name in line
+            continue
+        if on:
+            m = re.match(r"\s+/\*([0-9a-f]{4})\*/\s+(.*?);", line)
+            if m:
+                out.append((int(m.group(1), 16), m.group(2).strip()))
+    return out
+
+
+def operand(tok, env):
+    tok = tok.strip().replace(".reuse", "")
+    neg = tok.startswith("-")
+    tok = tok.lstrip("-")
+    ab = tok.startswith("|")
+    tok = tok.strip("|")
+    if re.fullmatch(r"U?R\d+", tok):
+        e = env.get(tok, ("leaf", tok))
+    elif tok in ("RZ", "URZ"):
+        e = ("const", "0")
+    else:
+        e = ("const", tok)
+    if ab:
+        e = ("abs", e)
+    if neg:
+        e = ("neg", e)
+    return e
+
+
+def canon(e):
+    """Canonical text of an expression: leaves anonymous, commutative operands sorted, and negations pulled out of
+    products ((-a) * b and a * (-b) round identically, so do fma(-a, b, c) and fma(a, -b, c))."""
+    s, neg = _canon(e)
+    return ("neg(" + s + ")") if neg else s
+
+
+def _canon(e):
+    k = e[0]
+    if k == "leaf":
+        return "x", False
+    if k == "const":
+        t = e[1]
+        return (t[1:], True) if t.startswith("-") else (t, False)
+    if k == "neg":
+        s, n = _canon(e[1])
+        return s, not n
+    if k == "abs":
+        s, _ = _canon(e[1])
+        return "abs(" + s + ")", False
+    if k in ("rcp", "sqrt", "ex2", "i2f"):
+        return k + "(" + canon(e[1]) + ")", False
+    if k == "FMUL":
+        parts = [_canon(a) for a in e[1:]]
+        return "mul(" + ",".join(sorted(p[0] for p in parts)) + ")", (sum(p[1] for p in parts) % 2 == 1)
+    if k == "FADD":
+        return "add(" + ",".join(sorted(canon(a) for a in e[1:])) + ")", False
+    if k == "FFMA":
+        parts = [_canon(a) for a in e[1:3]]
+        prod = ",".join(sorted(p[0] for p in parts))
+        sign = "-" if sum(p[1] for p in parts) % 2 == 1 else "+"
+        return "fma(" + sign + prod + ";" + canon(e[3]) + ")", False
+    return k, False
+
+
+def run(body, stop_pc=None):
+    """Symbolic execution in listing order (predicates and branches ignored: meant for straight-line stretches)."""
+    env = {}
+    for pc, ins in body:
+        if stop_pc is not None and pc >= stop_pc:
+            break
+        ins = re.sub(r"^@!?U?P\d+\s+", "", ins)
+        parts = ins.split(None, 1)
+        op = parts[0].split(".")[0]
+        args = [a.strip() for a in parts[1].split(",")] if len(parts) > 1 else []
+        if op in FP and len(args) == FP[op] + 1:
+            env[args[0]] = (op,) + tuple(operand(a, env) for a in args[1:])
+        elif op == "MUFU" and len(args) == 2:
+            kind = parts[0].split(".")[1].lower()
+            env[args[0]] = (kind, operand(args[1], env))
+        elif op == "I2FP" and len(args) == 2:
+            env[args[0]] = ("i2f", operand(args[1], env))
+        elif op in ("MOV", "UMOV", "R2UR", "IMAD") and len(args) >= 2 and op != "IMAD":
+            env[args[0]] = operand(args[1], env)
+        elif op in ("TEX", "TLD", "TLD4") and len(args) > 1:
+            for a in args[:2]:                  # TEX RZ, Rdst, ... : the fetched texel is a fresh leaf
+                if re.fullmatch(r"R\d+", a):
+                    env.pop(a, None)
+        elif args and re.fullmatch(r"U?R\d+", args[0]):
+            env.pop(args[0], None)              # anything else that writes a register: a fresh leaf
+            if op in ("LDS", "LDG", "LDC", "LDCU", "LDL") and ".128" in parts[0]:
+                base = int(args[0].lstrip("UR"))
+                for k in range(4):
+                    env.pop(f"R{base + k}", None)
+            if op in ("LDS", "LDG", "LDC", "LDCU", "LDL") and ".64" in parts[0]:
+                base = int(args[0].lstrip("UR"))
+                for k in range(2):
+                    env.pop(f"R{base + k}", None)
+    return env
+
+
+def main():
+    import hashlib
+
+    path, name = sys.argv[1], sys.argv[2]
+    body = function_body(path, name)
+    tex = [i for i, (_, ins) in enumerate(body) if ins.startswith("TEX")]
+    assert tex, "no TEX in " + name
+    print(f"# {name}: {len(body)} instructions, {len(tex)} texture fetches")
+    # every fetch whose coordinates are fma(numerator, rcp(Z), 0.5) is a source sample of an (inlined) NCC
+    for t in tex:
+        env = run(body[:t])
+        args = [a.strip() for a in body[t][1].split(None, 1)[1].split(",")]
+        base = int(args[2].lstrip("R")) + (1 if "ARRAY" in body[t][1] else 0)     # layered fetch: the layer comes first
+        cs = [canon(env.get(f"R{base + k}", ("leaf", "?"))) for k in (0, 1)]
+        if not all(c.startswith("fma(") and c.endswith(";0.5)") and "rcp(" in c for c in cs):
+            continue
+        print(f"  TEX at {body[t][0]:#07x}: coordinates R{base},R{base + 1}  nodes {cs[0].count('(')},{cs[1].count('(')}  "
+              f"sha1 {hashlib.sha1(cs[0].encode()).hexdigest()[:16]} {hashlib.sha1(cs[1].encode()).hexdigest()[:16]}")
+        if len(sys.argv) > 3:
+            print(cs[0])
+    # the bilateral weight: argument of every MUFU.EX2 that depends on a square root (exp(-sqrt(i^2+j^2)/.. - |r-r0|/..))
+    seen = {}
+    for k, (pc, ins) in enumerate(body):
+        if ins.startswith("MUFU.EX2"):
+            env = run(body[:k])
+            c = canon(operand(ins.split(",")[1], env))
+            if "sqrt(" in c:
+                seen.setdefault(c, []).append(pc)
+    for c, pcs in seen.items():
+        print(f"  EX2 argument at {[hex(p) for p in pcs][:4]}: {c}")
+
+
+if __name__ == "__main__":
+    main()

@@ -23,6 +23,11 @@ VARIANTS = {
     "bh2mb8": ["-DPM_BH=2", "-DPM_MIN_BLOCKS=8"],
     "bh8mb2": ["-DPM_BH=8", "-DPM_MIN_BLOCKS=2"],
     "bh8mb1": ["-DPM_BH=8", "-DPM_MIN_BLOCKS=1"],
+    # fidelity experiments (pm_core.cuh): the reference's own operation order for the tap coordinates / for the whole NCC
+    # and the geometric cost. Use with float32 view storage (--tex f32): 8-bit storage filters differently.
+    "litwarp": ["-DPM_LITERAL_WARP=1"],
+    "literal": ["-DPM_LITERAL_NCC=1"],
+    "literal_mb2": ["-DPM_LITERAL_NCC=1", "-DPM_MIN_BLOCKS=2"],
 }
 
 
