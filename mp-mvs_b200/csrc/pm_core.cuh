@@ -91,7 +91,6 @@ struct PmView {
 struct PmFrame {
     float fx, fy, cx, cy;      // K[0], K[4], K[2], K[5] of the reference view
     float ifx, ify;            // 1/fx, 1/fy
-    float fx_over_fy;          // K[0]/K[4] (cu:86)
     float R[9];                // reference rotation (cu:89-97, 308-316)
     float depth_min, depth_max;
     float spat_k;              // -log2(e) / (2 sigma_spatial^2)
@@ -188,13 +187,9 @@ PM_HD float pm_dot3(const pm_f4& a, const pm_f4& b) { return a.x * b.x + a.y * b
 
 // ComputeDepthfromPlaneHypothesis, cu:84-87
 PM_HD float pm_depth_from_plane(const PmFrame& F, const pm_f4& pl, int x, int y) {
-#if PM_LITERAL_NCC
-    // K[0] / K[4] is formed on the device by the reference (an approximate division under --use_fast_math, not
-    // necessarily 1 when the two are equal), not on the host
+    // K[0] / K[4] is formed on the device by the reference: under --use_fast_math an approximate division (x * rcp(x) is
+    // not always 1 when the two focal lengths are equal), so it is formed here and not on the host
     return -pl.w * F.fx / ((x - F.cx) * pl.x + (F.fx / F.fy) * (y - F.cy) * pl.y + F.fx * pl.z);
-#else
-    return -pl.w * F.fx / ((x - F.cx) * pl.x + F.fx_over_fy * (y - F.cy) * pl.y + F.fx * pl.z);
-#endif
 }
 // GetPlane2Origin, cu:163-176
 PM_HD float pm_plane_distance(const PmFrame& F, int x, int y, float depth, const pm_f4& n) {

@@ -86,7 +86,6 @@ inline PmFrame pm_make_frame(const mpmvs_camera& c, int n, float depth_min, floa
     PmFrame F{};
     F.fx = c.K[0]; F.fy = c.K[4]; F.cx = c.K[2]; F.cy = c.K[5];
     F.ifx = 1.0f / c.K[0]; F.ify = 1.0f / c.K[4];
-    F.fx_over_fy = c.K[0] / c.K[4];
     for (int i = 0; i < 9; ++i) F.R[i] = c.R[i];
     F.depth_min = depth_min; F.depth_max = depth_max;
     const double log2e = 1.4426950408889634;
