@@ -89,6 +89,9 @@ struct mpmvs_problem {
     int2* d_vxy = nullptr; int3* d_tris = nullptr; pm_f4* d_tri_planes = nullptr; size_t vtx_cap = 0, tri_cap = 0;
     unsigned int* d_prior_count = nullptr;
     std::vector<short> h_cell_xy; std::vector<unsigned char> h_cell_n;
+#if PM_LITERAL_NCC == 2
+    float lit_table[20];               // pm_literal_table evaluated on this device (mpmvs_create)
+#endif
 };
 
 namespace {
@@ -111,6 +114,11 @@ PmFrame make_frame(const mpmvs_problem* p) {
         if (p->cams[i].width != p->cache->W || p->cams[i].height != p->cache->H) soft = 1;
     F.soft_clamp = soft;
     F.tex = (unsigned long long)p->cache->tex;
+#if PM_LITERAL_NCC == 2
+    for (int k = 0; k < 18; ++k) F.lit_sd[k / 6][k % 6] = p->lit_table[k];
+    F.lit_rcp_spatial = p->lit_table[18];
+    F.lit_rcp_color = p->lit_table[19];
+#endif
     return F;
 }
 
@@ -376,6 +384,17 @@ int mpmvs_create(int device, void* stream, mpmvs_problem** out) {
     }
     cudaEventCreate(&p->ev0);
     cudaEventCreate(&p->ev1);
+#if PM_LITERAL_NCC == 2
+    {
+        float* d = nullptr;
+        cudaError_t e = cudaMalloc((void**)&d, sizeof(p->lit_table));
+        if (e == cudaSuccess) e = pm_launch_literal_table(p->sigma_spatial, p->sigma_color, d, p->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(p->lit_table, d, sizeof(p->lit_table), cudaMemcpyDeviceToHost, p->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+        cudaFree(d);
+        if (e != cudaSuccess) { mpmvs_destroy(p); return (int)e; }
+    }
+#endif
     *out = p;
     return MPMVS_OK;
 }

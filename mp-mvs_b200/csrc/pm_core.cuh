@@ -55,6 +55,11 @@
 // from 1, so the last bit of every weight and the order of the additions are worth up to 1e-2 in cost: there the
 // difference to the reference comes from here, not from the coordinates (tests/tools/literal_ncc_check.py).
 // Still hoisted (bit-identical whether done once or per call): the reference-side sums and the centre pixel.
+// 2: the same arithmetic with the taps unrolled again. Level 1 gets the reference's FMA contraction by imitating its loop
+// structure and leaving the fusing to the compiler; level 2 writes down what the reference's SASS does -- every product it
+// rounds is pm_rmul, every fused multiply-add pm_ffma (device: __fmul_rn / __fmaf_rn, never re-fused; host: plain unfused
+// arithmetic, i.e. the oracle's) -- and takes the six spatial tap distances of a scale from a table the device computed
+// (MUFU.SQRT results, PmFrame::lit_sd) instead of folding them at compile time.
 #define PM_LITERAL_NCC 0
 #endif
 #if PM_LITERAL_NCC
@@ -106,6 +111,10 @@ struct PmFrame {
     float K[9], t[3], C[3];    // the rest of the reference camera (R is above): ComputeHomography, BackProjectPoint2W, ProjectPoint
     int one;                   // 1, as a run-time value: keeps the tap offsets of the literal weight out of constant folding
     float sigma_spatial, sigma_color;
+    // level 2: sqrt(i^2 + j^2) of the six tap classes at the three scales and the two reciprocals of the weight, as the
+    // DEVICE evaluates them under --use_fast_math (pm_literal_table; the host emulation fills in libm's values)
+    float lit_sd[3][6];
+    float lit_rcp_spatial, lit_rcp_color;
 #endif
 };
 
@@ -147,6 +156,33 @@ PM_HD void pm_count(unsigned long long* ctr, uint32_t n) {
     *ctr += n;
 #endif
 }
+
+#if PM_LITERAL_NCC == 2
+// Pinned roundings (see PM_LITERAL_NCC): on the device exactly one instruction each, never contracted with a neighbour.
+#if defined(__CUDA_ARCH__)
+PM_HD float pm_rmul(float a, float b) { return __fmul_rn(a, b); }
+PM_HD float pm_radd(float a, float b) { return __fadd_rn(a, b); }
+PM_HD float pm_ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+#else
+PM_HD float pm_rmul(float a, float b) { return a * b; }
+PM_HD float pm_radd(float a, float b) { return a + b; }
+PM_HD float pm_ffma(float a, float b, float c) { return a * b + c; }   // the oracle is plain C: every product rounded
+#endif
+// i^2 + j^2 of a tap in units of (step/2)^2 -> its class 0..5: 2, 10, 18, 26, 34, 50
+PM_HD constexpr int pm_tap_class(int u, int v) {
+    return (u * u + v * v == 2) ? 0 : (u * u + v * v == 10) ? 1 : (u * u + v * v == 18) ? 2 : (u * u + v * v == 26) ? 3 : (u * u + v * v == 34) ? 4 : 5;
+}
+// The table behind PmFrame::lit_sd / lit_rcp_*: 18 square roots and 2 reciprocals, evaluated wherever this is compiled
+// (device: MUFU.SQRT / MUFU.RCP under --use_fast_math, as in the reference's kernels; `one` = 1.0f at run time keeps the
+// compiler from folding them).
+PM_HD void pm_literal_table(float one, float sigma_spatial, float sigma_color, float* out20) {
+    const int cls[6] = {2, 10, 18, 26, 34, 50};
+    for (int s = 0; s < 3; ++s)
+        for (int k = 0; k < 6; ++k) out20[s * 6 + k] = sqrtf((float)(cls[k] << (2 * s)) * one);
+    out20[18] = one / (2.0f * sigma_spatial * sigma_spatial);
+    out20[19] = one / (2.0f * sigma_color * sigma_color);
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------ RNG
 // XORWOW with cuRAND's start state for curand_init(seed, 0, 0) and curand_uniform's output map, so a
@@ -279,13 +315,60 @@ PM_HD float pm_weight_literal(float x_dist, float y_dist, float pix, float cente
     return expf(-spatial_dist / (2.0f * sigma_spatial * sigma_spatial) - color_dist / (2.0f * sigma_color * sigma_color));
 }
 #endif
+#if PM_LITERAL_NCC == 2
+// The same weight as the reference's SASS evaluates it (RefNccMap / BlackPixelUpdate in oracle/_ref):
+//   EX2(1.4426950216 * FFMA(-SQRT(i^2 + j^2), RCP(2 s_s s_s), -(|r - r0| * RCP(2 s_c s_c))))
+// with the square root and the reciprocals taken from the device-computed table. Host: the oracle's expression.
+template <int SCALE>
+PM_HD float pm_weight_pinned(const PmFrame& F, int cls, float r, float r0) {
+#if defined(__CUDA_ARCH__)
+    const float t = __fmul_rn(fabsf(r - r0), F.lit_rcp_color);
+    const float u = __fmaf_rn(-F.lit_sd[SCALE][cls], F.lit_rcp_spatial, -t);
+    return exp2f(__fmul_rn(u, 1.4426950216293334961f));
+#else
+    return expf(-F.lit_sd[SCALE][cls] / (2.0f * F.sigma_spatial * F.sigma_spatial) - fabsf(r - r0) / (2.0f * F.sigma_color * F.sigma_color));
+#endif
+}
+#endif
 
 template <int SCALE, class Ctx, int TAPS = 6>
 PM_HD PmRefStats pm_ref_stats(const Ctx& c, const PmFrame& F) {
     constexpr int HS = 1 << SCALE;  // step/2: taps at (2a-5)*HS
     PmRefStats st;
     st.r0 = c.ref(0, 0);
-#if PM_LITERAL_NCC
+#if PM_LITERAL_NCC == 2
+    {   // reference-side half of cu:355-405 with pinned roundings: FMUL r*w, FADD sum w, FFMA(r, r*w, .), FADD sum r*w per
+        // tap, rows added with FADD; 1/sum through MUFU.RCP, mean by FMUL, variance FFMA(sum rr, inv, -mean^2)
+        float sum_ref = 0.0f, sum_ref_ref = 0.0f, weight_sum = 0.0f;
+#pragma unroll
+        for (int a = 0; a < TAPS; ++a) {
+            const int i = (2 * a - (TAPS - 1)) * HS;
+            float row_ref = 0.0f, row_ref_ref = 0.0f, row_weight = 0.0f;
+#pragma unroll
+            for (int b = 0; b < TAPS; ++b) {
+                const int j = (2 * b - (TAPS - 1)) * HS;
+                const float r = c.ref(i, j);
+                const float w = pm_weight_pinned<SCALE>(F, pm_tap_class(2 * a - (TAPS - 1), 2 * b - (TAPS - 1)), r, st.r0);
+                const float rw = pm_rmul(w, r);
+                row_ref = pm_radd(row_ref, rw);
+                row_ref_ref = pm_ffma(rw, r, row_ref_ref);
+                row_weight = pm_radd(row_weight, w);
+            }
+            sum_ref = pm_radd(sum_ref, row_ref);
+            sum_ref_ref = pm_radd(sum_ref_ref, row_ref_ref);
+            weight_sum = pm_radd(weight_sum, row_weight);
+        }
+        st.inv_sw = 1.0f / weight_sum;
+        st.mean_r = pm_rmul(sum_ref, st.inv_sw);
+#if defined(__CUDA_ARCH__)
+        st.var_r = __fmaf_rn(sum_ref_ref, st.inv_sw, -__fmul_rn(st.mean_r, st.mean_r));
+#else
+        sum_ref_ref *= st.inv_sw;
+        st.var_r = sum_ref_ref - st.mean_r * st.mean_r;
+#endif
+        return st;
+    }
+#elif PM_LITERAL_NCC
     {   // the reference-side half of cu:355-405: rows of the window are summed on their own, then added up
         // run-time loop bounds, not unrolled: the reference's loops are (cu:340-346,365,373), and the compiler's choice of
         // which products to fuse into FMAs follows the loop structure (unrolled taps get their spatial term hoisted and
@@ -411,7 +494,58 @@ PM_HD float pm_ncc(const Ctx& c, const PmFrame& F, const PmRefStats& st, int v, 
     if (pcx >= V.w || pcx < 0.0f || pcy >= V.h || pcy < 0.0f) return 2.0f;  // cu:351-353
     if (st.var_r < 1e-5f) return 2.0f;                                     // cu:407 (hypothesis-invariant)
     ++nexec;
-#if PM_LITERAL_NCC
+#if PM_LITERAL_NCC == 2
+    // source-side half of cu:355-413 as the reference's SASS evaluates it, taps unrolled. Per row: FMUL H0 px, H3 px, H6 px.
+    // Per tap: numerators FADD(H2, FFMA(H1, py, H0 px)), ...; MUFU.RCP(Z); coordinates FFMA(X, rcp, 0.5); FMUL r*w, FMUL s*w,
+    // FADD sum(w s), FFMA(s, s*w, .), FFMA(s, r*w, .). Host: the oracle's divisions and unfused products, same order.
+    float sum_src = 0.0f, sum_src_src = 0.0f, sum_ref_src = 0.0f;
+#pragma unroll
+    for (int a = 0; a < TAPS; ++a) {
+        const int i = (2 * a - (TAPS - 1)) * HS;
+        const float px = (float)(x + i);
+        const float hx = pm_rmul(Hm[0], px), hy = pm_rmul(Hm[3], px), hz = pm_rmul(Hm[6], px);
+        float row_src = 0.0f, row_src_src = 0.0f, row_ref_src = 0.0f;
+#pragma unroll
+        for (int b = 0; b < TAPS; ++b) {
+            const int j = (2 * b - (TAPS - 1)) * HS;
+            const float py = (float)(y + j);
+            const float X = pm_radd(pm_ffma(Hm[1], py, hx), Hm[2]);
+            const float Y = pm_radd(pm_ffma(Hm[4], py, hy), Hm[5]);
+            const float Z = pm_radd(pm_ffma(Hm[7], py, hz), Hm[8]);
+#if defined(__CUDA_ARCH__)
+            const float rz = 1.0f / Z;                                     // MUFU.RCP under --use_fast_math
+            const float s = c.src(v, __fmaf_rn(X, rz, 0.5f), __fmaf_rn(Y, rz, 0.5f));
+#else
+            const float s = c.src(v, X / Z + 0.5f, Y / Z + 0.5f);
+#endif
+            const float r = c.ref(i, j);
+            const float w = pm_weight_pinned<SCALE>(F, pm_tap_class(2 * a - (TAPS - 1), 2 * b - (TAPS - 1)), r, st.r0);
+            const float sw = pm_rmul(w, s), rw = pm_rmul(w, r);
+            row_src = pm_radd(row_src, sw);
+            row_src_src = pm_ffma(sw, s, row_src_src);
+            row_ref_src = pm_ffma(rw, s, row_ref_src);
+        }
+        sum_src = pm_radd(sum_src, row_src);
+        sum_src_src = pm_radd(sum_src_src, row_src_src);
+        sum_ref_src = pm_radd(sum_ref_src, row_ref_src);
+    }
+    sum_src = pm_rmul(sum_src, st.inv_sw);
+#if defined(__CUDA_ARCH__)
+    const float var_src = __fmaf_rn(sum_src_src, st.inv_sw, -__fmul_rn(sum_src, sum_src));
+    sum_ref_src = __fmul_rn(sum_ref_src, st.inv_sw);
+    if (var_src < 1e-5f) return 2.0f;
+    const float covar_src_ref = __fmaf_rn(-st.mean_r, sum_src, sum_ref_src);
+    const float inv_dev = 1.0f / sqrtf(__fmul_rn(st.var_r, var_src));       // MUFU.SQRT, MUFU.RCP
+    return fmaxf(0.0f, fminf(2.0f, __fmaf_rn(-covar_src_ref, inv_dev, 1.0f)));
+#else
+    sum_src_src *= st.inv_sw;
+    sum_ref_src *= st.inv_sw;
+    const float var_src = sum_src_src - sum_src * sum_src;
+    if (var_src < 1e-5f) return 2.0f;
+    const float covar_src_ref = sum_ref_src - st.mean_r * sum_src;
+    return fmaxf(0.0f, fminf(2.0f, 1.0f - covar_src_ref / sqrtf(st.var_r * var_src)));
+#endif
+#elif PM_LITERAL_NCC
     // source-side half of cu:355-413
     const int step = 2 * HS * F.one, radius = (TAPS - 1) * step / 2;     // run-time bounds: see pm_ref_stats
     float sum_src = 0.0f, sum_src_src = 0.0f, sum_ref_src = 0.0f;

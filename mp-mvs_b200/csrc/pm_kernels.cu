@@ -375,6 +375,18 @@ cudaError_t pm_launch_export_depth(const pm_f4* planes, float* out, int W, int H
     return cudaGetLastError();
 }
 
+#if PM_LITERAL_NCC == 2
+namespace {
+__global__ void pm_literal_table_kernel(float one, float sigma_spatial, float sigma_color, float* out20) {
+    pm_literal_table(one, sigma_spatial, sigma_color, out20);
+}
+}  // namespace
+cudaError_t pm_launch_literal_table(float sigma_spatial, float sigma_color, float* out20_dev, cudaStream_t st) {
+    pm_literal_table_kernel<<<1, 1, 0, st>>>(1.0f, sigma_spatial, sigma_color, out20_dev);
+    return cudaGetLastError();
+}
+#endif
+
 cudaError_t pm_launch_uniform_stream(unsigned long long seed, int x, int y, int n, float* out, cudaStream_t st) {
     pm_uniform_stream_kernel<<<1, 1, 0, st>>>(seed, x, y, n, out);
     return cudaGetLastError();

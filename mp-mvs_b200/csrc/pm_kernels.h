@@ -18,6 +18,10 @@ cudaError_t pm_launch_geom_map(const PmFrame& F, const PmView* gviews, const pm_
 cudaError_t pm_launch_convert(const void* in, size_t in_pitch, int in_is_u8, void* out, int out_fmt, int W, int H, cudaStream_t st);
 cudaError_t pm_launch_export_depth(const pm_f4* planes, float* out, int W, int H, int pitch_floats, cudaStream_t st);
 cudaError_t pm_launch_uniform_stream(unsigned long long seed, int x, int y, int n, float* out, cudaStream_t st);
+#if PM_LITERAL_NCC == 2
+// 18 tap distances + 2 reciprocals as the device evaluates them (pm_core.cuh: pm_literal_table) -> PmFrame::lit_*
+cudaError_t pm_launch_literal_table(float sigma_spatial, float sigma_color, float* out20_dev, cudaStream_t st);
+#endif
 // planar-prior stage (pm_prior.cu)
 cudaError_t pm_launch_pick_vertices(const float* costs, const float* geom, int W, int H, int geom_variant, short2* out_xy,
                                     unsigned char* out_n, cudaStream_t st);

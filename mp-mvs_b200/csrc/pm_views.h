@@ -98,6 +98,17 @@ inline PmFrame pm_make_frame(const mpmvs_camera& c, int n, float depth_min, floa
     for (int i = 0; i < 3; ++i) { F.t[i] = c.t[i]; F.C[i] = c.C[i]; }
     F.one = 1;
     F.sigma_spatial = sigma_spatial; F.sigma_color = sigma_color;
+#if PM_LITERAL_NCC == 2
+    {   // host values (libm); the CUDA library overwrites them with the device's own (pm_capi.cu: literal_table)
+        float t[20];
+        pm_literal_table(1.0f, sigma_spatial, sigma_color, t);
+        for (int k = 0; k < 18; ++k) F.lit_sd[k / 6][k % 6] = t[k];
+        F.lit_rcp_spatial = t[18]; F.lit_rcp_color = t[19];
+    }
+#else
+    for (int k = 0; k < 18; ++k) F.lit_sd[k / 6][k % 6] = 0.f;
+    F.lit_rcp_spatial = F.lit_rcp_color = 0.f;
+#endif
 #endif
     return F;
 }

@@ -171,8 +171,9 @@ def test_restructurings_are_bit_identical(libs):
                 np.testing.assert_array_equal(x, y)
 
 
+@pytest.mark.parametrize("level", [1, 2])
 @pytest.mark.parametrize("name", CASES)
-def test_literal_variant_is_bit_identical_to_the_oracle(libs, name):
+def test_literal_variant_is_bit_identical_to_the_oracle(libs, name, level):
     """-DPM_LITERAL_NCC=1 (pm_core.cuh): homography, tap coordinates, bilateral weights, NCC sums and the geometric cost in
     the reference's own operation order. Instantiated on the host, the product's per-pixel templates must then reproduce
     the literal restatement (oracle/pm_oracle.c) BIT FOR BIT over whole runs in all three modes -- every plane, cost,
@@ -180,7 +181,8 @@ def test_literal_variant_is_bit_identical_to_the_oracle(libs, name):
     build too (the two builds differ only inside `#if PM_LITERAL_*`)."""
     from conftest import build_emul as be
 
-    libs.LIBS["emul_literal"] = (be("_literal", ["-DPM_LITERAL_NCC=1"]), "emu_")
+    # level 1: run-time tap loops, the compiler fuses; level 2: unrolled taps, every rounding pinned (host: unfused, as the oracle)
+    libs.LIBS["emul_literal"] = (be("_literal" if level == 1 else "_literal2", [f"-DPM_LITERAL_NCC={level}"]), "emu_")
     c = make_case(name)
     o = libs.Oracle("cpu").set_problem(c["images"], c["cams"])
     e = libs.Oracle("emul_literal").set_problem(c["images"], c["cams"])

@@ -7,8 +7,9 @@ expression tree of chosen registers and prints it in a canonical form (commutati
 that the reference's build (cuobjdump -sass oracle/_ref/libmpmvs_ref.so) and ours can be diffed modulo register
 allocation and scheduling.
 
-    python tests/tools/sass_expr.py ref.sass  RefNccMap        # prints the trees feeding the first source TEX in a loop
+    python tests/tools/sass_expr.py ref.sass  RefNccMap        # hashes of the source-fetch coordinates, weight exponents
     python tests/tools/sass_expr.py ours.sass pm_ncc_map_kernelILi0ELb0ELb0
+    python tests/tools/sass_expr.py compare ref.sass BlackPixelUpdate ours.sass pm_sweep_kernelILi0ELb0ELb0
 """
 import re
 import sys
@@ -25,7 +26,7 @@ def function_body(path, name):
             on = name in line
             continue
         if on:
-            m = re.match(r"\s+/\*([0-9a-f]{4})\*/\s+(.*?);", line)
+            m = re.match(r"\s+/\*([0-9a-f]{4,6})\*/\s+(.*?);", line)
             if m:
                 out.append((int(m.group(1), 16), m.group(2).strip()))
     return out
@@ -153,5 +154,59 @@ def main():
         print(f"  EX2 argument at {[hex(p) for p in pcs][:4]}: {c}")
 
 
+def source_coordinate_trees(path, name):
+    """Canonical trees of the x coordinate of every source-sample fetch (fma(numerator, rcp(Z), 0.5)) of a kernel."""
+    body = function_body(path, name)
+    out = []
+    for t, (_, ins) in enumerate(body):
+        if not ins.startswith("TEX"):
+            continue
+        env = run(body[:t])
+        args = [a.strip() for a in ins.split(None, 1)[1].split(",")]
+        base = int(args[2].lstrip("R")) + (1 if "ARRAY" in ins else 0)
+        c = canon(env.get(f"R{base}", ("leaf", "?")))
+        if c.startswith("fma(") and c.endswith(";0.5)") and "rcp(" in c:
+            out.append(c)
+    return out
+
+
+def subtrees(s):
+    stack, out = [], set()
+    for i, ch in enumerate(s):
+        if ch == "(":
+            j = i
+            while j > 0 and (s[j - 1].isalnum() or s[j - 1] == "_"):
+                j -= 1
+            stack.append(j)
+        elif ch == ")":
+            out.add(s[stack.pop():i + 1])
+    return out
+
+
+def compare(ref_path, ref_name, our_path, our_name):
+    """Are the source coordinates the same expression in both kernels? Equal trees, or equal once ONE subtree of ours is
+    taken as a leaf (a hypothesis that is still in registers in our kernel where the reference reloads it from memory)."""
+    ref = source_coordinate_trees(ref_path, ref_name)[0]
+    ours = source_coordinate_trees(our_path, our_name)
+    print(f"reference {ref_name}: {ref.count('(')} nodes; ours {our_name}: {len(ours)} source fetches")
+    verdicts = {}
+    for c in ours:
+        if c == ref:
+            v = "identical"
+        else:
+            v = "DIFFERENT"
+            have = subtrees(ref)
+            for k in sorted((k for k in subtrees(c) if k not in have), key=len, reverse=True):
+                if c.replace(k, "x") == ref:
+                    v = "identical once this is a leaf: " + (k[:120] + "..." if len(k) > 120 else k)
+                    break
+        verdicts[v] = verdicts.get(v, 0) + 1
+    for v, n in verdicts.items():
+        print(f"  {n:3d} x {v}")
+    return all(not v.startswith("DIFFERENT") for v in verdicts)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) == 6 and sys.argv[1] == "compare":
+        sys.exit(0 if compare(*sys.argv[2:6]) else 1)
     main()

@@ -28,6 +28,9 @@ VARIANTS = {
     "litwarp": ["-DPM_LITERAL_WARP=1"],
     "literal": ["-DPM_LITERAL_NCC=1"],
     "literal_mb2": ["-DPM_LITERAL_NCC=1", "-DPM_MIN_BLOCKS=2"],
+    # level 2: the same arithmetic with unrolled taps, every rounding pinned to what the reference's SASS does
+    "literal2": ["-DPM_LITERAL_NCC=2"],
+    "literal2_mb2": ["-DPM_LITERAL_NCC=2", "-DPM_MIN_BLOCKS=2"],
 }
 
 
