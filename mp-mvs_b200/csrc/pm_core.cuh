@@ -163,6 +163,9 @@ PM_HD void pm_count(unsigned long long* ctr, uint32_t n) {
 PM_HD float pm_rmul(float a, float b) { return __fmul_rn(a, b); }
 PM_HD float pm_radd(float a, float b) { return __fadd_rn(a, b); }
 PM_HD float pm_ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+// MUFU.RCP / MUFU.SQRT as such: `1.0f / sqrtf(x)` would be turned into one MUFU.RSQ, which the reference does not execute
+__device__ __forceinline__ float pm_rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float pm_sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 #else
 PM_HD float pm_rmul(float a, float b) { return a * b; }
 PM_HD float pm_radd(float a, float b) { return a + b; }
@@ -513,7 +516,7 @@ PM_HD float pm_ncc(const Ctx& c, const PmFrame& F, const PmRefStats& st, int v, 
             const float Y = pm_radd(pm_ffma(Hm[4], py, hy), Hm[5]);
             const float Z = pm_radd(pm_ffma(Hm[7], py, hz), Hm[8]);
 #if defined(__CUDA_ARCH__)
-            const float rz = 1.0f / Z;                                     // MUFU.RCP under --use_fast_math
+            const float rz = pm_rcp_approx(Z);
             const float s = c.src(v, __fmaf_rn(X, rz, 0.5f), __fmaf_rn(Y, rz, 0.5f));
 #else
             const float s = c.src(v, X / Z + 0.5f, Y / Z + 0.5f);
@@ -535,7 +538,7 @@ PM_HD float pm_ncc(const Ctx& c, const PmFrame& F, const PmRefStats& st, int v, 
     sum_ref_src = __fmul_rn(sum_ref_src, st.inv_sw);
     if (var_src < 1e-5f) return 2.0f;
     const float covar_src_ref = __fmaf_rn(-st.mean_r, sum_src, sum_ref_src);
-    const float inv_dev = 1.0f / sqrtf(__fmul_rn(st.var_r, var_src));       // MUFU.SQRT, MUFU.RCP
+    const float inv_dev = pm_rcp_approx(pm_sqrt_approx(__fmul_rn(st.var_r, var_src)));   // MUFU.SQRT, then MUFU.RCP
     return fmaxf(0.0f, fminf(2.0f, __fmaf_rn(-covar_src_ref, inv_dev, 1.0f)));
 #else
     sum_src_src *= st.inv_sw;
