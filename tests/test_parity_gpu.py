@@ -466,3 +466,29 @@ def test_live_full_schedule_vs_reference(capi, oracle, pkg, planar, geom_planar)
     # three chained stages (up to five Runs) of a chaotic algorithm: same-seed agreement decays from ~99 % per Run
     assert np.median(agree) > 0.94 and min(agree) > 0.90
     assert np.median(dacc) <= 0.5 and max(dacc) <= 1.5
+
+
+# ------------------------------------------------------------------------------------------ fidelity build (literal2)
+@pytest.mark.xfail(strict=False, reason="literal2 was prepared on CPU and checked against the reference's SASS only (profiles/"
+                                        "r01_literal_variant.md): its first GPU run is this test; the suite does not depend on it")
+def test_literal2_half_sweeps_bit_identical(oracle):
+    """-DPM_LITERAL_NCC=2 (variant library literal2): the reference's own arithmetic with unrolled taps and pinned roundings.
+    Claim under test: started from the reference's state, EVERY half-sweep reproduces the reference's planes, costs and
+    view masks bit for bit (the shipped kernels: 94-99 % of the planes), and so does a whole same-seed Run()."""
+    import json
+    import subprocess
+    import sys
+
+    need_ref(oracle)
+    lib = os.path.join(ROOT, "mp-mvs_b200", "variants", "libmpmvs_b200_literal2.so")
+    if not os.path.exists(lib):
+        pytest.skip("variant library not built (python tools/build_variants.py literal2)")
+    env = dict(os.environ, MPMVS_LIB_VARIANT="literal2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "variant_fidelity.py")], env=env, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    data = json.loads(r.stdout.strip().splitlines()[-1])
+    print("literal2 fidelity:", json.dumps(data["cases"]))
+    for name, c in data["cases"].items():
+        assert c["half_sweep_planes_min"] >= 0.9995 and c["half_sweep_costs_min"] >= 0.9995 and c["half_sweep_views_min"] >= 0.9995, (name, c)
+        assert c["run_planes_identical"] >= 0.995, (name, c)

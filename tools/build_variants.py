@@ -44,6 +44,9 @@ def build(name):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     names = sys.argv[1:] or list(VARIANTS)
+    failed = 0
     with ThreadPoolExecutor(8) as ex:
         for name, rc, err in ex.map(build, names):
             print(name, "ok" if rc == 0 else "FAILED " + err)
+            failed += rc != 0
+    sys.exit(1 if failed else 0)
