@@ -1,0 +1,68 @@
+"""The fidelity build (-DPM_LITERAL_NCC=2, mp-mvs_b200/variants/libmpmvs_b200_literal2.so) must keep COMPILING to the
+reference's arithmetic: under --use_fast_math bit-identity on the GPU (tests/test_parity_gpu.py::
+test_literal2_build_is_bit_identical_to_the_reference) depends on which products end up fused into FMAs, and that is only
+visible in the SASS. This CPU test disassembles both builds (cuobjdump, no GPU) and compares the floating-point expression
+trees with tests/tools/sass_expr.py, so an edit of pm_core.cuh that changes a rounding is caught where there is no GPU."""
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "tests", "tools"))
+
+REF = os.path.join(ROOT, "oracle", "_ref", "libmpmvs_ref.so")
+LIT = os.path.join(ROOT, "mp-mvs_b200", "variants", "libmpmvs_b200_literal2.so")
+CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+
+
+@pytest.fixture(scope="module")
+def sass(tmp_path_factory):
+    if not (os.path.exists(REF) and os.path.exists(LIT) and os.path.exists(CUOBJDUMP)):
+        pytest.skip("needs oracle/_ref/libmpmvs_ref.so, the literal2 variant library (build()) and cuobjdump")
+    d = tmp_path_factory.mktemp("sass")
+    out = {}
+    for tag, lib in (("ref", REF), ("lit", LIT)):
+        out[tag] = str(d / f"{tag}.sass")
+        with open(out[tag], "w") as f:
+            subprocess.check_call([CUOBJDUMP, "-sass", lib], stdout=f)
+    return out
+
+
+@pytest.mark.parametrize("scale", [0, 1, 2])
+def test_source_coordinates_are_the_reference_expression(sass, scale):
+    """ComputeHomography + ComputeCorrespondingPoint + 0.5 (cu:228-288,375-378): all 36 unrolled source fetches of our sweep
+    kernel carry the expression tree of the reference's BlackPixelUpdate (identical, or identical once the plane distance
+    that is still in registers at that point is taken as the leaf it is in the reference's first two inlined copies)."""
+    import sass_expr
+
+    ours = sass_expr.source_coordinate_trees(sass["lit"], f"pm_sweep_kernelILi{scale}ELb0ELb0")
+    assert len(ours) == 36
+    refs = sass_expr.source_coordinate_trees(sass["ref"], "BlackPixelUpdate")
+    assert len(refs) >= 3                                    # cost vector, current plane, refinement: three inlined copies
+    assert set(refs) == set(sass_expr.source_coordinate_trees(sass["ref"], "RedPixelUpdate"))
+    assert set(ours) <= set(refs), "a source coordinate of the fidelity build is not one of the reference's expressions"
+    assert sass_expr.compare(sass["ref"], "BlackPixelUpdate", sass["lit"], f"pm_sweep_kernelILi{scale}ELb0ELb0")
+
+
+def test_ncc_test_hook_matches_too(sass):
+    import sass_expr
+
+    ref = sass_expr.source_coordinate_trees(sass["ref"], "RefNccMap")
+    ours = sass_expr.source_coordinate_trees(sass["lit"], "pm_ncc_map_kernelILi0ELb0ELb0")
+    assert len(ours) == 36 and len(set(ref)) == 1 and set(ours) == set(ref)
+
+
+def test_no_rsqrt_in_the_ncc_tail(sass):
+    """1 / sqrt(var_r var_s) must stay MUFU.SQRT followed by MUFU.RCP as in the reference (cu:411-412 compiles to that),
+    not one MUFU.RSQ: the test hook kernel contains the NCC and nothing else that takes a square root."""
+    import sass_expr
+
+    body = [ins for _, ins in sass_expr.function_body(sass["lit"], "pm_ncc_map_kernelILi0ELb0ELb0")]
+    assert not any("MUFU.RSQ" in i for i in body)
+    assert any("MUFU.SQRT" in i for i in body) and any("MUFU.RCP" in i for i in body)
+    ref = [ins for _, ins in sass_expr.function_body(sass["ref"], "RefNccMap")]
+    assert not any("MUFU.RSQ" in i for i in ref)
