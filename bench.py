@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- depth-map throughput of the PatchMatch hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload eth3d|dtu|plane] [--tex u8|f32|f16]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload eth3d|dtu|plane] [--tex u8|f32|f16] [--fidelity fast|exact]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (config.workload): the configuration the metric is quoted on (BASELINE.json configs[2]) -- synthetic
@@ -403,7 +403,7 @@ def run_ours(args, rank, world, local_rank, prob, barrier, allmax):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": prob["label"], "width": W, "height": H, "src_views": nsrc,
                    "passes": "ProcessProblem(geom=0, planar=1): photometric Run (scales 2,1,0 x 3 it) + planar-prior stage + prior Run (3 it)",
-                   "view_storage": args.tex, "lib_variant": os.environ.get("MPMVS_LIB_VARIANT", "default"),
+                   "view_storage": args.tex, "lib_variant": os.environ.get("MPMVS_LIB_VARIANT", "default"), "fidelity": args.fidelity,
                    "l2": "inputs_larger_than_l2 (11 views = %.0f MB + %.0f MB state vs 126 MB L2)" % (n * W * H * (1 if args.tex == "u8" else 4) / 1e6, W * H * 76 / 1e6),
                    "parallelism": f"refs sharded over {world} gpu(s), no data-path collective in this pass"},
         "in_flight": depth,
@@ -535,8 +535,14 @@ def main():
     ap.add_argument("--trace", action="store_true", help="write the host-side call timeline of the e2e region to gpurun_out/")
     ap.add_argument("--in-flight", type=int, default=2, help="reference images kept in flight per GPU (1 = the reference's sequential order)")
     ap.add_argument("--tex", default="u8", choices=["f32", "f16", "u8"], help="storage format of the views in HBM")
+    ap.add_argument("--fidelity", default="fast", choices=["fast", "exact"],
+                    help="fast: the shipped kernels; exact: the fidelity build (variants/libmpmvs_b200_literal2.so, float32 storage), "
+                         "bit-identical to the reference's kernels (profiles/r01_literal_variant.md)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 1)
+    if args.fidelity == "exact":          # the library is chosen when mpmvs_b200.capi is first imported (run_ours)
+        os.environ["MPMVS_LIB_VARIANT"] = "literal2"
+        args.tex = "f32"
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -133,7 +133,12 @@ def main():
     ap.add_argument("--seed", type=int, default=0x2333)
     ap.add_argument("--in-flight", type=int, default=8, help="reference images in flight per GPU (host threads: the planar-prior triangulation is host work)")
     ap.add_argument("--fusion", type=int, default=1, help="fuse the depth maps on rank 0's GPU and write MPMVS_model.ply")
+    ap.add_argument("--fidelity", default="fast", choices=["fast", "exact"],
+                    help="exact: the fidelity build of the kernels (variants/libmpmvs_b200_literal2.so, float32 view storage): the "
+                         "reference's kernel results bit for bit, about 25 %% slower than the shipped kernels")
     args = ap.parse_args()
+    if args.fidelity == "exact":          # the library is chosen when mpmvs_b200.capi is first imported (below)
+        os.environ["MPMVS_LIB_VARIANT"] = "literal2"
     import torch
 
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -152,7 +157,7 @@ def main():
     pcfg = pipeline.PipelineConfig(geom_iterations=int(cfg["Geometric consistency iterations"]), max_src=int(cfg["Max source images num"]),
                                    seed=args.seed, planar_prior=bool(int(cfg["Planer prior"])),
                                    geom_planar_prior=bool(int(cfg["Geometric consistency planer prior"])),
-                                   tex_format=capi.TEX_F32 if resized else capi.TEX_U8, in_flight=args.in_flight)
+                                   tex_format=capi.TEX_F32 if (resized or args.fidelity == "exact") else capi.TEX_U8, in_flight=args.in_flight)
     p = pipeline.DensePipeline(entries, cams, images, pcfg, rank=rank, world=world, device=local, dist=dist)
     p.setup()
     t1 = time.time()
