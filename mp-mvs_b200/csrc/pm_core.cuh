@@ -59,7 +59,10 @@
 // structure and leaving the fusing to the compiler; level 2 writes down what the reference's SASS does -- every product it
 // rounds is pm_rmul, every fused multiply-add pm_ffma (device: __fmul_rn / __fmaf_rn, never re-fused; host: plain unfused
 // arithmetic, i.e. the oracle's) -- and takes the six spatial tap distances of a scale from a table the device computed
-// (MUFU.SQRT results, PmFrame::lit_sd) instead of folding them at compile time.
+// (MUFU.SQRT results, PmFrame::lit_sd) instead of folding them at compile time. Level 2 is the FIDELITY BUILD of the
+// library (`make exact`, variants/libmpmvs_b200_literal2.so): measured bit-identical to the reference's kernels on the
+// B200 -- every half-sweep, whole runs, the full-size run -- about 25 % slower than the shipped form
+// (profiles/r01_literal_variant.md; tests: test_emul_vs_oracle.py, test_sass_equivalence.py, test_parity_gpu.py).
 #define PM_LITERAL_NCC 0
 #endif
 #if PM_LITERAL_NCC
