@@ -500,3 +500,24 @@ def test_literal2_build_is_bit_identical_to_the_reference(oracle):
     print("literal2 at full size:", json.dumps(full))
     assert full["run_planes_identical"] == 1.0 and full["run_costs_identical"] == 1.0 and full["max_abs_depth_diff"] == 0.0, full
     assert full["photometric_run_ms"] < 0.6 * full["reference_run_ms"], full      # measured 398 ms against 1 062 ms
+
+
+@pytest.mark.xfail(strict=False, reason="the planar-prior and geometric-consistency modes of the fidelity build are bit-identical to the "
+                                        "oracle on the CPU and compile to the reference's instruction mix, but the round's GPU budget ended "
+                                        "before they could be run: this is their first run; the suite does not depend on it")
+def test_literal2_prior_and_geom_runs_bit_identical(oracle):
+    import json
+    import subprocess
+    import sys
+
+    need_ref(oracle)
+    lib = os.path.join(ROOT, "mp-mvs_b200", "variants", "libmpmvs_b200_literal2.so")
+    if not os.path.exists(lib):
+        pytest.skip("variant library not built (make -C mp-mvs_b200/csrc exact)")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "variant_fidelity.py"), "--modes"],
+                       env=dict(os.environ, MPMVS_LIB_VARIANT="literal2"), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    modes = json.loads(r.stdout.strip().splitlines()[-1])["modes"]
+    print("literal2, other modes:", json.dumps(modes))
+    for name, c in modes.items():
+        assert all(v == 1.0 for v in c.values()), (name, c)

@@ -5,6 +5,7 @@ shipped in-tree library), so every build gets its own process:
 
     MPMVS_LIB_VARIANT=literal2 python tests/tools/variant_fidelity.py
     python tests/tools/variant_fidelity.py                    # the shipped kernels, for comparison
+    ... --modes                                                # also whole planar-prior and geometric-consistency runs
 
 For the three parity cases, float32 view storage: every half-sweep of a photometric Run() started from the reference's own
 state (fraction of bit-identical planes / costs / view masks among the updated pixels, minimum and mean over the 18
@@ -65,7 +66,44 @@ def main():
             "run_planes_identical": float(np.all(pa == pb, -1).mean()), "run_costs_identical": float((ca == cb).mean()),
             "run_ms": float(ms), "run_ms_reference": float(ms_ref)}
         pm.destroy(); ref.destroy()
+    if "--modes" in sys.argv:
+        out["modes"] = other_modes()
     print(json.dumps(out))
+
+
+def other_modes():
+    """Whole same-seed planar-prior Run() (on top of a photometric one, state resident) and geometric-consistency Run() on
+    the three cases: fractions of bit-identical planes / costs / geometric costs against the reference."""
+    from cases import prior_planes, src_depths, world_state_from_gt
+
+    res = {}
+    for name in CASES:
+        c = make_case(name)
+        pm = capi.PatchMatch(0).set_problem(c["images"], c["cams"])
+        ref = oracle_py.Oracle("ref").set_problem(c["images"], c["cams"])
+        for o in (pm, ref):
+            o.set_geom_consistency_params(False, False)
+            o.run(SEED)
+            o.set_planar_prior_params()
+            o.set_geom_consistency_params(False, True)
+            o.set_prior(*prior_planes(c))
+            o.run(SEED + 1)
+        (pa, ca), (pb, cb) = pm.result(), ref.result()
+        r = {"prior_run_planes_identical": float(np.all(pa == pb, -1).mean()), "prior_run_costs_identical": float((ca == cb).mean())}
+        pm.destroy(); ref.destroy()
+        pm = capi.PatchMatch(0).set_problem(c["images"], c["cams"])
+        ref = oracle_py.Oracle("ref").set_problem(c["images"], c["cams"])
+        for o in (pm, ref):
+            o.set_geom_consistency_params(True, False)
+            o.set_src_depths(src_depths(c, 0.002))
+            o.set_state(*world_state_from_gt(c))
+            o.run(SEED + 2)
+        ga, gb = pm.result(geom=True), ref.result(geom=True)
+        r.update({"geom_run_planes_identical": float(np.all(ga[0] == gb[0], -1).mean()), "geom_run_costs_identical": float((ga[1] == gb[1]).mean()),
+                  "geom_run_geom_costs_identical": float((ga[2] == gb[2]).mean())})
+        pm.destroy(); ref.destroy()
+        res[name] = r
+    return res
 
 
 if __name__ == "__main__":
