@@ -23,6 +23,9 @@ metric = W*H*steps / seconds, summed over ranks.
            sweep launches x 16 B / their summed device time (CUDA events between launches on the launching stream);
            peak = 4 bilinear fetches/clk/SM x 148 SMs x sm_max_mhz x 16 B -- the nominal TMU rate, which
            tools/tex_microbench.cu reaches on this GPU (3.98/clk/SM, profiles/r01_tex_microbench.log).
+  fidelity_exact : (N=1) the same step through the fidelity build -- the same kernels compiled with the reference's own
+           operation order (variants/libmpmvs_b200_literal2.so, float32 storage), bit-identical to the reference's kernels on
+           the B200 -- measured by a child process (`bench.py --fidelity exact`) after the headline; --no-exact-arm skips it.
   cpu_baseline : the plain-C oracle port (oracle/pm_oracle.c, all host cores) on a centre crop of the same views
            (photometric Run only: the port is the checker of the kernels, not a pipeline).
   --impl reference : the reference's own CUDA path (oracle/_ref/libmpmvs_ref.so = /root/reference/src/PatchMatch.cu
@@ -524,6 +527,33 @@ def run_reference(args, prob):
     }
 
 
+def exact_arm(args) -> dict:
+    """The same step through the fidelity build (--fidelity exact: variants/libmpmvs_b200_literal2.so, float32 storage,
+    bit-identical to the reference's kernels), measured by a child process after this one has released the GPU -- the
+    library is chosen at import time. Reported beside the headline, never instead of it: any failure ends up in `error`."""
+    lib = os.path.join(ROOT, "mp-mvs_b200", "variants", "libmpmvs_b200_literal2.so")
+    if not os.path.exists(lib):
+        return {"error": "variants/libmpmvs_b200_literal2.so not built (make -C mp-mvs_b200/csrc exact)"}
+    cmd = [sys.executable, os.path.abspath(__file__), "--fidelity", "exact", "--no-cpu-baseline", "--steps", str(args.steps),
+           "--warmup", str(args.warmup), "--workload", args.workload, "--in-flight", str(args.in_flight)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MPMVS_LIB_VARIANT")}
+    try:
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=420)
+        if r.returncode != 0 or not r.stdout.strip():
+            return {"error": f"child exited {r.returncode}: {r.stderr.strip()[-300:]}"}
+        j = json.loads(r.stdout.strip().splitlines()[-1])
+        keep = ("value", "unit", "ms_per_step", "e2e", "gpu_launches", "kernel_ms_per_step", "clocks", "checksum_mean_cost", "accuracy_2_5_10cm")
+        res = {k: j[k] for k in keep if k in j}
+        res["roofline_frac"] = j.get("roofline", {}).get("frac")
+        res["executed_taps_per_step"] = j.get("roofline", {}).get("executed_taps_per_step")
+        res["config"] = {k: j["config"][k] for k in ("view_storage", "lib_variant", "fidelity") if k in j.get("config", {})}
+        res["note"] = ("same workload, steps and timing rules as the headline; kernels bit-identical to the reference's "
+                       "(tests/test_parity_gpu.py::test_literal2_build_is_bit_identical_to_the_reference)")
+        return res
+    except Exception as e:          # noqa: BLE001 -- a reported extra must never take the headline down
+        return {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -538,6 +568,7 @@ def main():
     ap.add_argument("--fidelity", default="fast", choices=["fast", "exact"],
                     help="fast: the shipped kernels; exact: the fidelity build (variants/libmpmvs_b200_literal2.so, float32 storage), "
                          "bit-identical to the reference's kernels (profiles/r01_literal_variant.md)")
+    ap.add_argument("--no-exact-arm", action="store_true", help="at N=1, skip the extra measurement of the fidelity build (fidelity_exact)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 1)
     if args.fidelity == "exact":          # the library is chosen when mpmvs_b200.capi is first imported (run_ours)
@@ -580,6 +611,8 @@ def main():
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(prob)
+        if world == 1 and args.fidelity == "fast" and not args.no_exact_arm:
+            out["fidelity_exact"] = exact_arm(args)
         print(json.dumps(out), flush=True)
     if dist is not None:
         dist.barrier()

@@ -73,3 +73,19 @@ def test_roofline_constants():
     assert bench.TAPS_PER_NCC == 36 and bench.BYTES_PER_TAP == 16 and bench.N_SM == 148 and bench.TEX_PER_CLK_SM == 4
     assert bench.ncu_traffic("eth3d") == pytest.approx(684e6)
     assert bench.ncu_traffic("dtu") is None
+
+
+def test_exact_arm_never_takes_the_headline_down():
+    """`fidelity_exact` is measured by a child process; whatever happens to it (here: no GPU) must come back as an `error`
+    entry, not as an exception in the process that prints the headline line."""
+    import types
+
+    from conftest import has_gpu
+
+    if has_gpu():
+        pytest.skip("only meaningful on a box without a GPU")
+    sys.path.insert(0, ROOT)
+    import bench
+
+    res = bench.exact_arm(types.SimpleNamespace(steps=1, warmup=1, workload="plane", in_flight=2))
+    assert set(res) == {"error"} and res["error"]
