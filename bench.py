@@ -548,7 +548,7 @@ def exact_arm(args) -> dict:
         res["executed_taps_per_step"] = j.get("roofline", {}).get("executed_taps_per_step")
         res["config"] = {k: j["config"][k] for k in ("view_storage", "lib_variant", "fidelity") if k in j.get("config", {})}
         res["note"] = ("same workload, steps and timing rules as the headline; kernels bit-identical to the reference's "
-                       "(tests/test_parity_gpu.py::test_literal2_build_is_bit_identical_to_the_reference)")
+                       "(tests/test_zz_fidelity_build_gpu.py::test_literal2_build_is_bit_identical_to_the_reference)")
         return res
     except Exception as e:          # noqa: BLE001 -- a reported extra must never take the headline down
         return {"error": f"{type(e).__name__}: {str(e)[:300]}"}

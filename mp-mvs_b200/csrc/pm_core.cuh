@@ -62,7 +62,7 @@
 // (MUFU.SQRT results, PmFrame::lit_sd) instead of folding them at compile time. Level 2 is the FIDELITY BUILD of the
 // library (`make exact`, variants/libmpmvs_b200_literal2.so): measured bit-identical to the reference's kernels on the
 // B200 -- every half-sweep, whole runs, the full-size run -- about 25 % slower than the shipped form
-// (profiles/r01_literal_variant.md; tests: test_emul_vs_oracle.py, test_sass_equivalence.py, test_parity_gpu.py).
+// (profiles/r01_literal_variant.md; tests: test_emul_vs_oracle.py, test_sass_equivalence.py, test_zz_fidelity_build_gpu.py).
 #define PM_LITERAL_NCC 0
 #endif
 #if PM_LITERAL_NCC

@@ -10,7 +10,7 @@ shipped in-tree library), so every build gets its own process:
 For the three parity cases, float32 view storage: every half-sweep of a photometric Run() started from the reference's own
 state (fraction of bit-identical planes / costs / view masks among the updated pixels, minimum and mean over the 18
 half-sweeps), then a whole same-seed Run() (fraction of bit-identical result planes and costs), and the device time of that
-Run() for both. tests/test_parity_gpu.py::test_literal2_half_sweeps_bit_identical reads the JSON.
+Run() for both. tests/test_zz_fidelity_build_gpu.py reads the JSON.
 """
 import json
 import os
