@@ -1,8 +1,8 @@
 """The fidelity build (-DPM_LITERAL_NCC=2, mp-mvs_b200/variants/libmpmvs_b200_literal2.so) must keep COMPILING to the
-reference's arithmetic: under --use_fast_math bit-identity on the GPU (
-the GPU test of the fidelity build) depends on which products end up fused into FMAs, and that is only
-visible in the SASS. (That GPU test is tests/test_zz_fidelity_build_gpu.py.) This CPU test disassembles both builds (cuobjdump, no GPU) and compares the floating-point expression
-trees with tests/tools/sass_expr.py, so an edit of pm_core.cuh that changes a rounding is caught where there is no GPU."""
+reference's arithmetic: under --use_fast_math its bit-identity with the reference on the GPU
+(tests/test_zz_fidelity_build_gpu.py) depends on which products end up fused into FMAs, and that is only visible in the
+SASS. This CPU test disassembles both builds (cuobjdump, no GPU) and compares the floating-point expression trees with
+tests/tools/sass_expr.py, so an edit of pm_core.cuh that changes a rounding is caught where there is no GPU."""
 import os
 import shutil
 import subprocess
