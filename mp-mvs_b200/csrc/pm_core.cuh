@@ -354,7 +354,9 @@ PM_HD PmRefStats pm_ref_stats(const Ctx& c, const PmFrame& F) {
             for (int b = 0; b < TAPS; ++b) {
                 const int j = (2 * b - (TAPS - 1)) * HS;
                 const float r = c.ref(i, j);
-                const float w = pm_weight_pinned<SCALE>(F, pm_tap_class(2 * a - (TAPS - 1), 2 * b - (TAPS - 1)), r, st.r0);
+                // the table holds the reference's 6 x 6 window; other windows (NCC microbenchmark only) take the square root at run time
+                const float w = TAPS == 6 ? pm_weight_pinned<SCALE>(F, pm_tap_class(2 * a - (TAPS - 1), 2 * b - (TAPS - 1)), r, st.r0)
+                                          : pm_weight_literal((float)(i * F.one), (float)(j * F.one), r, st.r0, F.sigma_spatial, F.sigma_color);
                 const float rw = pm_rmul(w, r);
                 row_ref = pm_radd(row_ref, rw);
                 row_ref_ref = pm_ffma(rw, r, row_ref_ref);
@@ -525,7 +527,8 @@ PM_HD float pm_ncc(const Ctx& c, const PmFrame& F, const PmRefStats& st, int v, 
             const float s = c.src(v, X / Z + 0.5f, Y / Z + 0.5f);
 #endif
             const float r = c.ref(i, j);
-            const float w = pm_weight_pinned<SCALE>(F, pm_tap_class(2 * a - (TAPS - 1), 2 * b - (TAPS - 1)), r, st.r0);
+            const float w = TAPS == 6 ? pm_weight_pinned<SCALE>(F, pm_tap_class(2 * a - (TAPS - 1), 2 * b - (TAPS - 1)), r, st.r0)
+                                      : pm_weight_literal((float)(i * F.one), (float)(j * F.one), r, st.r0, F.sigma_spatial, F.sigma_color);
             const float sw = pm_rmul(w, s), rw = pm_rmul(w, r);
             row_src = pm_radd(row_src, sw);
             row_src_src = pm_ffma(sw, s, row_src_src);
