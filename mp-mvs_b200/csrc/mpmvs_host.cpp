@@ -84,7 +84,7 @@ void GenerateSampleList(const ConfigParams& config, std::vector<Scene>& Scenes) 
         file >> scene.refID;
         // ids index `Scenes` (PatchMatch.cpp:871-890 does Scenes[srcID[i]] unchecked): a truncated or out-of-order file
         // must end in a message, not in an out-of-bounds access
-        if (!file || scene.refID < (int)Scenes.size()) throw std::runtime_error("malformed pair.txt (reference id of entry " + std::to_string(i) + "): " + path);
+        if (!file || scene.refID < (int)Scenes.size() || scene.refID > (1 << 24)) throw std::runtime_error("malformed pair.txt (reference id of entry " + std::to_string(i) + "): " + path);
         scene.srcID.push_back(scene.refID);
         while (scene.refID > (int)Scenes.size()) Scenes.emplace_back();     // gaps in the ids: estimate == false
         int num_src = 0;

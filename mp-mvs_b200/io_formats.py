@@ -183,6 +183,8 @@ def _read_pairs(it, max_src: int) -> List[SceneEntry]:
         ref = int(next(it))
         if ref < len(scenes):                      # scenes are indexed by image id: ids must ascend
             raise ValueError(f"reference id {ref} out of order")
+        if ref > 1 << 24:                          # the gap up to `ref` is padded with empty scenes (cpp:87-91)
+            raise ValueError(f"reference id {ref} is not an image id")
         sc = SceneEntry(ref_id=ref, src_ids=[ref])
         while ref > len(scenes):
             scenes.append(SceneEntry())

@@ -52,6 +52,7 @@ def test_main_reports_missing_inputs(tmp_path):
     ("2\n1\n1 0 1.0\n0\n1 1 1.0\n", "malformed pair.txt"),         # ids out of order: Scenes[id] would be another image
     ("1\n0\n2 1 1.0 x\n", "malformed pair.txt"),                    # a source entry that is not a number
     ("2\n0\n1 7 1.0\n1\n1 0 1.0\n", "no entry of its own"),        # a source id beyond the list (Scenes[7] in the reference)
+    ("2\n0\n1 1 1.0\n2147483647\n1 0 1.0\n", "malformed pair.txt"),  # an id that would pad two billion empty scenes
 ])
 def test_main_refuses_malformed_inputs(tmp_path, pairs, message):
     """The reference indexes Scenes[srcID[i]] and reads pair.txt / cams unchecked (PatchMatch.cpp:67-143,871-890); the host
@@ -77,6 +78,45 @@ def test_main_refuses_truncated_camera_and_dmb(tmp_path):
     dump.mkdir()
     r = subprocess.run([MAIN, yaml, "--check-inputs", str(dump)], capture_output=True, text=True)
     assert r.returncode == 1 and "malformed camera file" in r.stdout, (r.returncode, r.stdout[-500:])
+
+
+def test_host_parsers_survive_mutated_inputs(tmp_path):
+    """Fuzz: truncated, shuffled and garbled pair.txt / camera files / .pgm images must end `mpmvs_main --check-inputs` with
+    exit code 0 or 1 (a message), never with a signal (segmentation fault, abort, bad_alloc escaping main)."""
+    import random
+
+    build_main()
+    sc, root, yaml = write_scene(tmp_path, 64, 48)
+    targets = [os.path.join(root, "pair.txt"), os.path.join(root, "cams", "00000000_cam.txt"), os.path.join(root, "images", "00000000.pgm")]
+    originals = {t: open(t, "rb").read() for t in targets}
+    rng = random.Random(7)
+    dump = tmp_path / "dump"
+    dump.mkdir()
+    codes = set()
+    for trial in range(40):
+        t = targets[trial % len(targets)]
+        data = bytearray(originals[t])
+        kind = rng.randrange(4)
+        if kind == 0:                                   # truncate
+            data = data[:rng.randrange(0, len(data))]
+        elif kind == 1:                                 # overwrite a stretch with random bytes
+            a = rng.randrange(0, len(data)); b = min(len(data), a + rng.randrange(1, 24))
+            data[a:b] = bytes(rng.randrange(256) for _ in range(b - a))
+        elif kind == 2:                                 # blow up a number
+            toks = data.split()
+            if toks:
+                toks[rng.randrange(len(toks))] = rng.choice([b"-1", b"99999999999", b"1e40", b"nan", b"2147483647"])
+                data = bytearray(b" ".join(toks))
+        else:                                           # duplicate a stretch
+            a = rng.randrange(0, len(data)); data[a:a] = data[a:a + rng.randrange(1, 64)]
+        with open(t, "wb") as f:
+            f.write(bytes(data))
+        r = subprocess.run([MAIN, yaml, "--check-inputs", str(dump)], capture_output=True, timeout=60)
+        codes.add(r.returncode)
+        assert r.returncode in (0, 1), (trial, t, kind, r.returncode, r.stdout[-300:], r.stderr[-300:])
+        with open(t, "wb") as f:
+            f.write(originals[t])
+    assert 1 in codes           # some of the mutations were refused with a message
 
 
 @pytest.mark.parametrize("max_size", [3200, 200])

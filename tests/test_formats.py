@@ -69,6 +69,7 @@ def test_pairs_rules(tmp_path):
     "2\n1\n1 0 1.0\n0\n1 1 1.0\n",            # ids out of order: scenes[id] would be another image
     "1\n0\n2 1 1.0 x\n",                       # not a number
     "2\n0\n1 7 1.0\n1\n1 0 1.0\n",            # a source without an entry (Scenes[7] in the reference, unchecked)
+    "2\n0\n1 1 1.0\n2147483647\n1 0 1.0\n",   # an id that would pad two billion empty scenes
 ])
 def test_pairs_malformed(tmp_path, text):
     p = str(tmp_path / "pair.txt")
