@@ -407,6 +407,7 @@ def run_ours(args, rank, world, local_rank, prob, barrier, allmax):
         "config": {"workload": prob["label"], "width": W, "height": H, "src_views": nsrc,
                    "passes": "ProcessProblem(geom=0, planar=1): photometric Run (scales 2,1,0 x 3 it) + planar-prior stage + prior Run (3 it)",
                    "view_storage": args.tex, "lib_variant": os.environ.get("MPMVS_LIB_VARIANT", "default"), "fidelity": args.fidelity,
+                   "arithmetic": capi.build_flavor(),
                    "l2": "inputs_larger_than_l2 (11 views = %.0f MB + %.0f MB state vs 126 MB L2)" % (n * W * H * (1 if args.tex == "u8" else 4) / 1e6, W * H * 76 / 1e6),
                    "parallelism": f"refs sharded over {world} gpu(s), no data-path collective in this pass"},
         "in_flight": depth,
@@ -546,7 +547,7 @@ def exact_arm(args) -> dict:
         res = {k: j[k] for k in keep if k in j}
         res["roofline_frac"] = j.get("roofline", {}).get("frac")
         res["executed_taps_per_step"] = j.get("roofline", {}).get("executed_taps_per_step")
-        res["config"] = {k: j["config"][k] for k in ("view_storage", "lib_variant", "fidelity") if k in j.get("config", {})}
+        res["config"] = {k: j["config"][k] for k in ("view_storage", "lib_variant", "fidelity", "arithmetic") if k in j.get("config", {})}
         res["note"] = ("same workload, steps and timing rules as the headline; kernels bit-identical to the reference's "
                        "(tests/test_zz_fidelity_build_gpu.py::test_literal2_build_is_bit_identical_to_the_reference)")
         return res

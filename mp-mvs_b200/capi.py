@@ -116,6 +116,8 @@ def lib() -> C.CDLL:
     L.mpmvs_error_string.argtypes = [C.c_int]
     L.mpmvs_error_string.restype = C.c_char_p
     L.mpmvs_version.restype = C.c_int
+    L.mpmvs_build_flavor.argtypes = []
+    L.mpmvs_build_flavor.restype = C.c_char_p
     _lib = L
     return L
 
@@ -123,6 +125,11 @@ def lib() -> C.CDLL:
 class PriorStats(C.Structure):
     _fields_ = [("n_vertices", C.c_int), ("n_triangles", C.c_int), ("n_prior_pixels", C.c_int), ("pick_ms", C.c_float),
                 ("delaunay_ms", C.c_float), ("raster_ms", C.c_float), ("total_ms", C.c_float)]
+
+
+def build_flavor() -> str:
+    """Which arithmetic the loaded library was compiled with: "shipped" or "literal2" (bit-identical to the reference's kernels)."""
+    return lib().mpmvs_build_flavor().decode()
 
 
 def _ck(rc: int, what: str):

@@ -356,6 +356,18 @@ extern "C" {
 
 int mpmvs_version(void) { return 100; }
 
+const char* mpmvs_build_flavor(void) {
+#if PM_LITERAL_NCC == 2
+    return "literal2";
+#elif PM_LITERAL_NCC == 1
+    return "literal";
+#elif PM_LITERAL_WARP
+    return "litwarp";
+#else
+    return "shipped";
+#endif
+}
+
 const char* mpmvs_error_string(int code) {
     switch (code) {
         case MPMVS_OK: return "ok";

@@ -48,6 +48,7 @@ def test_literal2_build_is_bit_identical_to_the_reference(oracle):
         return json.loads(r.stdout.strip().splitlines()[-1])
 
     data = tool("variant_fidelity.py")
+    assert data["arithmetic"] == "literal2", data["library"]        # the child really loaded the fidelity build
     print("literal2 fidelity:", json.dumps(data["cases"]))
     for name, c in data["cases"].items():
         assert c["half_sweep_planes_min"] == 1.0 and c["half_sweep_costs_min"] == 1.0 and c["half_sweep_views_min"] == 1.0, (name, c)

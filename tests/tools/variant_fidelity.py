@@ -29,7 +29,7 @@ from parity_checks import colour_mask  # noqa: E402
 
 
 def main():
-    out = {"variant": os.environ.get("MPMVS_LIB_VARIANT", "shipped"), "library": capi.LIB_PATH, "cases": {}}
+    out = {"variant": os.environ.get("MPMVS_LIB_VARIANT", "shipped"), "library": capi.LIB_PATH, "arithmetic": capi.build_flavor(), "cases": {}}
     for name in CASES:
         c = make_case(name)
         pm = capi.PatchMatch(0).set_problem(c["images"], c["cams"])

@@ -23,7 +23,7 @@ def main():
     prob = bench.load_problem("eth3d", 0, 1, lambda: None)
     tex = "u8" if "--tex" in sys.argv and sys.argv[sys.argv.index("--tex") + 1] == "u8" else "f32"
     imgs = [i.astype(np.uint8) for i in prob["images"]] if tex == "u8" else prob["images"]
-    out = {"variant": os.environ.get("MPMVS_LIB_VARIANT", "shipped"), "tex": tex, "load_s": round(time.time() - t0, 1)}
+    out = {"variant": os.environ.get("MPMVS_LIB_VARIANT", "shipped"), "arithmetic": capi.build_flavor(), "tex": tex, "load_s": round(time.time() - t0, 1)}
     pm = capi.PatchMatch(0).set_tex_format(capi.TEX_U8 if tex == "u8" else capi.TEX_F32).set_problem(imgs, prob["cams"])
     pm.set_geom_consistency_params(False, False)
     pm.run(1)                                           # warm-up
