@@ -586,6 +586,9 @@ int main(int argc, char* argv[]) {
             return 0;
         }
         std::cout << "Input data path:" << config.input_folder << "\nOutput data path:" << config.output_folder << std::endl;
+        std::cout << "Kernels: " << mpmvs_build_flavor() << " arithmetic"
+                  << (!strcmp(mpmvs_build_flavor(), "shipped") ? " (mpmvs_main_exact runs the build that is bit-identical to the reference's kernels)" : "")
+                  << std::endl;
         mkdir(config.output_folder.c_str(), 0777);
         std::vector<Scene> Scenes;
         GenerateSampleList(config, Scenes);
