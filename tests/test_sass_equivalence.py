@@ -66,3 +66,20 @@ def test_no_rsqrt_in_the_ncc_tail(sass):
     assert any("MUFU.SQRT" in i for i in body) and any("MUFU.RCP" in i for i in body)
     ref = [ins for _, ins in sass_expr.function_body(sass["ref"], "RefNccMap")]
     assert not any("MUFU.RSQ" in i for i in ref)
+
+
+# md5 of the instruction text of the fidelity build's pipeline kernels (sass_expr.pipeline_checksum) as they were when
+# tests/test_zz_fidelity_build_gpu.py measured them bit-identical to the reference on a B200 (nvcc 12.9.86, sm_100a).
+VERIFIED_ON_GPU = "38deed19ed9b343b41d98f8be66a9bca"
+
+
+def test_fidelity_kernels_are_the_ones_verified_on_the_gpu(sass):
+    """Any edit that changes an instruction of the fidelity build's sweep / init / finalize kernels lands here first: run
+    tests/test_zz_fidelity_build_gpu.py on a B200 again and, if it is still bit-identical, record the new checksum
+    (`python tests/tools/sass_expr.py md5 <cuobjdump -sass of the library>`). Comments and host code do not change it."""
+    import sass_expr
+
+    nvcc = subprocess.run([os.path.join(os.path.dirname(CUOBJDUMP), "nvcc"), "--version"], capture_output=True, text=True).stdout
+    if "V12.9.86" not in nvcc:
+        pytest.skip("recorded for nvcc 12.9.86; another compiler schedules differently")
+    assert sass_expr.pipeline_checksum(sass["lit"]) == VERIFIED_ON_GPU

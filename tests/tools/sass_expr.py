@@ -206,7 +206,27 @@ def compare(ref_path, ref_name, our_path, our_name):
     return all(not v.startswith("DIFFERENT") for v in verdicts)
 
 
+PIPELINE_KERNELS = ("pm_sweep_kernel", "pm_init_kernel", "pm_ncc_map_kernel", "pm_geom_map", "pm_depth_normal", "pm_filter")
+
+
+def pipeline_checksum(path):
+    """md5 over the instruction text (addresses kept, encodings dropped) of the kernels the pipeline runs, in listing order."""
+    import hashlib
+
+    h, on = hashlib.md5(), False
+    for line in open(path):
+        if "Function :" in line:
+            on = any(k in line for k in PIPELINE_KERNELS)
+            continue
+        if on and re.match(r"\s+/\*[0-9a-f]{4,6}\*/", line):
+            h.update((re.sub(r"/\* 0x[0-9a-f]+ \*/", "", line).rstrip() + "\n").encode())
+    return h.hexdigest()
+
+
 if __name__ == "__main__":
+    if len(sys.argv) == 3 and sys.argv[1] == "md5":
+        print(pipeline_checksum(sys.argv[2]))
+        sys.exit(0)
     if len(sys.argv) == 6 and sys.argv[1] == "compare":
         sys.exit(0 if compare(*sys.argv[2:6]) else 1)
     main()
