@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- depth-map throughput of the PatchMatch hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload eth3d|dtu|plane] [--tex u8|f32|f16] [--fidelity fast|exact]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload eth3d|dtu|plane] [--arithmetic exact|fast] [--tex u8|f32|f16]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (config.workload): the configuration the metric is quoted on (BASELINE.json configs[2]) -- synthetic
@@ -23,9 +23,10 @@ metric = W*H*steps / seconds, summed over ranks.
            sweep launches x 16 B / their summed device time (CUDA events between launches on the launching stream);
            peak = 4 bilinear fetches/clk/SM x 148 SMs x sm_max_mhz x 16 B -- the nominal TMU rate, which
            tools/tex_microbench.cu reaches on this GPU (3.98/clk/SM, profiles/r01_tex_microbench.log).
-  fidelity_exact : (N=1) the same step through the fidelity build -- the same kernels compiled with the reference's own
-           operation order (variants/libmpmvs_b200_literal2.so, float32 storage), bit-identical to the reference's kernels on
-           the B200 -- measured by a child process (`bench.py --fidelity exact`) after the headline; --no-exact-arm skips it.
+  arithmetic : the headline is the EXACT arithmetic of the library (mpmvs_set_arithmetic, include/mpmvs_b200.h): the
+           reference's operations one for one, float32 view storage, results bit-identical to the reference's kernels
+           (tests/test_zz_fidelity_build_gpu.py). `arithmetic_fast` (N=1) reports the same step through the library's fast
+           arithmetic with 8-bit view storage (statistically equal results) beside it; --no-fast-arm skips it.
   cpu_baseline : the plain-C oracle port (oracle/pm_oracle.c, all host cores) on a centre crop of the same views
            (photometric Run only: the port is the checker of the kernels, not a pipeline).
   --impl reference : the reference's own CUDA path (oracle/_ref/libmpmvs_ref.so = /root/reference/src/PatchMatch.cu
@@ -276,20 +277,22 @@ class Prof(list):
         self.timing, self.count = timing, count
 
 
-def run_ours(args, rank, world, local_rank, prob, barrier, allmax):
+def run_ours(args, rank, world, local_rank, prob, barrier, allmax, arithmetic=None, tex=None):
     import torch
     from mpmvs_b200 import capi
 
+    arithmetic = arithmetic or args.arithmetic
+    tex = tex or args.tex
     torch.cuda.set_device(local_rank)
     W, H, n = prob["width"], prob["height"], len(prob["images"])
-    fmt = {"f32": capi.TEX_F32, "f16": capi.TEX_F16, "u8": capi.TEX_U8}[args.tex]
+    fmt = {"f32": capi.TEX_F32, "f16": capi.TEX_F16, "u8": capi.TEX_U8}[tex]
     depth = max(1, args.in_flight)
     # each handle works on its own torch stream, so torch events bracket its work
     lo, hi = torch.cuda.Stream.priority_range()      # (0, -5) on B200: lower number = more urgent
     streams = [torch.cuda.Stream(device=local_rank, priority=max(hi, lo - (depth - 1 - k))) for k in range(depth)]
-    handles = [capi.PatchMatch(device=local_rank, stream=s.cuda_stream).set_tex_format(fmt) for s in streams]
+    handles = [capi.PatchMatch(device=local_rank, stream=s.cuda_stream).set_arithmetic(arithmetic).set_tex_format(fmt) for s in streams]
     # host images: uint8 grey levels as decoded from the JPEGs when the storage is 8-bit, else float32; pinned
-    host_imgs = [i.astype(np.uint8) for i in prob["images"]] if args.tex == "u8" else prob["images"]
+    host_imgs = [i.astype(np.uint8) for i in prob["images"]] if tex == "u8" else prob["images"]
     pin_imgs = [torch.from_numpy(i).pin_memory() for i in host_imgs]
     pin_np = [t.numpy() for t in pin_imgs]
     h_planes = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory() for _ in handles]
@@ -406,9 +409,11 @@ def run_ours(args, rank, world, local_rank, prob, barrier, allmax):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": prob["label"], "width": W, "height": H, "src_views": nsrc,
                    "passes": "ProcessProblem(geom=0, planar=1): photometric Run (scales 2,1,0 x 3 it) + planar-prior stage + prior Run (3 it)",
-                   "view_storage": args.tex, "lib_variant": os.environ.get("MPMVS_LIB_VARIANT", "default"), "fidelity": args.fidelity,
-                   "arithmetic": capi.build_flavor(),
-                   "l2": "inputs_larger_than_l2 (11 views = %.0f MB + %.0f MB state vs 126 MB L2)" % (n * W * H * (1 if args.tex == "u8" else 4) / 1e6, W * H * 76 / 1e6),
+                   "view_storage": tex, "lib_variant": os.environ.get("MPMVS_LIB_VARIANT", "default"),
+                   "arithmetic": handles[0].arithmetic, "library": capi.build_flavor(),
+                   "parity": ("bit-identical to the reference's kernels (tests/test_zz_fidelity_build_gpu.py)" if arithmetic == "exact" and tex == "f32"
+                              else "statistically equal to the reference's kernels (DESIGN.md section 5)"),
+                   "l2": "inputs_larger_than_l2 (11 views = %.0f MB + %.0f MB state vs 126 MB L2)" % (n * W * H * (1 if tex == "u8" else 4) / 1e6, W * H * 76 / 1e6),
                    "parallelism": f"refs sharded over {world} gpu(s), no data-path collective in this pass"},
         "in_flight": depth,
         "e2e": {"value": round(e2e, 4), "unit": "Mpix/s", "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in pin_imgs) + 112 * n),
@@ -528,28 +533,18 @@ def run_reference(args, prob):
     }
 
 
-def exact_arm(args) -> dict:
-    """The same step through the fidelity build (--fidelity exact: variants/libmpmvs_b200_literal2.so, float32 storage,
-    bit-identical to the reference's kernels), measured by a child process after this one has released the GPU -- the
-    library is chosen at import time. Reported beside the headline, never instead of it: any failure ends up in `error`."""
-    lib = os.path.join(ROOT, "mp-mvs_b200", "variants", "libmpmvs_b200_literal2.so")
-    if not os.path.exists(lib):
-        return {"error": "variants/libmpmvs_b200_literal2.so not built (make -C mp-mvs_b200/csrc exact)"}
-    cmd = [sys.executable, os.path.abspath(__file__), "--fidelity", "exact", "--no-cpu-baseline", "--steps", str(args.steps),
-           "--warmup", str(args.warmup), "--workload", args.workload, "--in-flight", str(args.in_flight)]
-    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MPMVS_LIB_VARIANT")}
+def fast_arm(args, rank, world, local_rank, prob, barrier, allmax) -> dict:
+    """The same step through the library's FAST arithmetic with 8-bit view storage (mpmvs_set_arithmetic; statistically equal
+    results), in this process after the headline. Reported beside the headline, never instead of it: any failure ends up in
+    `error`."""
     try:
-        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=420)
-        if r.returncode != 0 or not r.stdout.strip():
-            return {"error": f"child exited {r.returncode}: {r.stderr.strip()[-300:]}"}
-        j = json.loads(r.stdout.strip().splitlines()[-1])
+        j = run_ours(args, rank, world, local_rank, prob, barrier, allmax, arithmetic="fast", tex="u8")
         keep = ("value", "unit", "ms_per_step", "e2e", "gpu_launches", "kernel_ms_per_step", "clocks", "checksum_mean_cost", "accuracy_2_5_10cm")
         res = {k: j[k] for k in keep if k in j}
         res["roofline_frac"] = j.get("roofline", {}).get("frac")
         res["executed_taps_per_step"] = j.get("roofline", {}).get("executed_taps_per_step")
-        res["config"] = {k: j["config"][k] for k in ("view_storage", "lib_variant", "fidelity", "arithmetic") if k in j.get("config", {})}
-        res["note"] = ("same workload, steps and timing rules as the headline; kernels bit-identical to the reference's "
-                       "(tests/test_zz_fidelity_build_gpu.py::test_literal2_build_is_bit_identical_to_the_reference)")
+        res["config"] = {k: j["config"][k] for k in ("view_storage", "arithmetic", "parity") if k in j.get("config", {})}
+        res["note"] = "same workload, steps and timing rules as the headline"
         return res
     except Exception as e:          # noqa: BLE001 -- a reported extra must never take the headline down
         return {"error": f"{type(e).__name__}: {str(e)[:300]}"}
@@ -565,16 +560,18 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--trace", action="store_true", help="write the host-side call timeline of the e2e region to gpurun_out/")
     ap.add_argument("--in-flight", type=int, default=2, help="reference images kept in flight per GPU (1 = the reference's sequential order)")
-    ap.add_argument("--tex", default="u8", choices=["f32", "f16", "u8"], help="storage format of the views in HBM")
-    ap.add_argument("--fidelity", default="fast", choices=["fast", "exact"],
-                    help="fast: the shipped kernels; exact: the fidelity build (variants/libmpmvs_b200_literal2.so, float32 storage), "
-                         "bit-identical to the reference's kernels (profiles/r01_literal_variant.md)")
-    ap.add_argument("--no-exact-arm", action="store_true", help="at N=1, skip the extra measurement of the fidelity build (fidelity_exact)")
+    ap.add_argument("--arithmetic", "--fidelity", dest="arithmetic", default="exact", choices=["exact", "fast"],
+                    help="exact (default): the reference's operations one for one, bit-identical results; fast: hoisted arithmetic, "
+                         "statistically equal results (mpmvs_set_arithmetic)")
+    ap.add_argument("--tex", default=None, choices=["f32", "f16", "u8"],
+                    help="storage format of the views in HBM (default: f32 with the exact arithmetic -- the reference's, and what its "
+                         "bit-identity needs -- and u8 with the fast one)")
+    ap.add_argument("--no-fast-arm", "--no-exact-arm", dest="no_fast_arm", action="store_true",
+                    help="at N=1, skip the extra measurement of the fast arithmetic (arithmetic_fast)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 1)
-    if args.fidelity == "exact":          # the library is chosen when mpmvs_b200.capi is first imported (run_ours)
-        os.environ["MPMVS_LIB_VARIANT"] = "literal2"
-        args.tex = "f32"
+    if args.tex is None:
+        args.tex = "f32" if args.arithmetic == "exact" else "u8"
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -612,8 +609,8 @@ def main():
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(prob)
-        if world == 1 and args.fidelity == "fast" and not args.no_exact_arm:
-            out["fidelity_exact"] = exact_arm(args)
+        if world == 1 and args.arithmetic == "exact" and not args.no_fast_arm:
+            out["arithmetic_fast"] = fast_arm(args, rank, world, local_rank, prob, barrier, allmax)
         print(json.dumps(out), flush=True)
     if dist is not None:
         dist.barrier()

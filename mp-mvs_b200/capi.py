@@ -22,6 +22,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libmpmvs_b200.so")
 if os.environ.get("MPMVS_LIB_VARIANT"):
     LIB_PATH = os.path.join(PKG_DIR, "variants", f"libmpmvs_b200_{os.environ['MPMVS_LIB_VARIANT']}.so")
 TEX_F32, TEX_F16, TEX_U8 = 0, 1, 2
+ARITH_EXACT, ARITH_FAST = 0, 1      # MPMVS_ARITH_*: both arithmetics are in the one library, a handle picks at run time
 
 _lib = None
 
@@ -32,7 +33,7 @@ class MpmvsError(RuntimeError):
 
 def build(verbose: bool = False) -> str:
     """Compile the sm_100a library in-tree (nvcc cross-compiles without a GPU)."""
-    cmd = ["make", "-s", "-C", os.path.join(PKG_DIR, "csrc")]
+    cmd = ["make", "-s", "-j", str(min(6, os.cpu_count() or 1)), "-C", os.path.join(PKG_DIR, "csrc")]
     subprocess.check_call(cmd, stdout=None if verbose else subprocess.DEVNULL)
     return LIB_PATH
 
@@ -108,6 +109,9 @@ def lib() -> C.CDLL:
         "mpmvs_prior_from_triangles": [vp, vp, i, vp, i, C.POINTER(i)],
         "mpmvs_get_prior": [vp, vp, vp],
         "mpmvs_get_prior_pixels": [vp, C.POINTER(i)],
+        "mpmvs_set_arithmetic": [vp, i],
+        "mpmvs_get_arithmetic": [vp, C.POINTER(i)],
+        "mpmvs_default_arithmetic": [],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -118,6 +122,8 @@ def lib() -> C.CDLL:
     L.mpmvs_version.restype = C.c_int
     L.mpmvs_build_flavor.argtypes = []
     L.mpmvs_build_flavor.restype = C.c_char_p
+    L.mpmvs_arithmetic_name.argtypes = [C.c_int]
+    L.mpmvs_arithmetic_name.restype = C.c_char_p
     _lib = L
     return L
 
@@ -128,8 +134,14 @@ class PriorStats(C.Structure):
 
 
 def build_flavor() -> str:
-    """Which arithmetic the loaded library was compiled with: "shipped" or "literal2" (bit-identical to the reference's kernels)."""
+    """What the loaded library holds: "exact+fast" (both arithmetics, chosen per handle at run time)."""
     return lib().mpmvs_build_flavor().decode()
+
+
+def default_arithmetic() -> str:
+    """The arithmetic a new handle starts with: "exact" (bit-identical to the reference's kernels) unless the environment
+    has MPMVS_ARITHMETIC=fast."""
+    return lib().mpmvs_arithmetic_name(lib().mpmvs_default_arithmetic()).decode()
 
 
 def _ck(rc: int, what: str):
@@ -253,6 +265,19 @@ class PatchMatch:
         _ck(lib().mpmvs_create(device, C.c_void_p(stream) if stream else None, C.byref(self.h)), "create")
         self.n = self.w = self.hgt = 0
         self._keep = []
+
+    # ------------------------------------------------------------------ arithmetic
+    def set_arithmetic(self, arithmetic):
+        """ARITH_EXACT / "exact" (default: the reference's operations bit for bit) or ARITH_FAST / "fast"."""
+        a = {"exact": ARITH_EXACT, "fast": ARITH_FAST}.get(arithmetic, arithmetic)
+        _ck(lib().mpmvs_set_arithmetic(self.h, int(a)), "set_arithmetic")
+        return self
+
+    @property
+    def arithmetic(self) -> str:
+        a = C.c_int()
+        _ck(lib().mpmvs_get_arithmetic(self.h, C.byref(a)), "get_arithmetic")
+        return lib().mpmvs_arithmetic_name(a.value).decode()
 
     # ------------------------------------------------------------------ inputs
     def set_tex_format(self, fmt: int):

@@ -2,7 +2,7 @@
 // config.yaml -> pair.txt -> stage 1 (multi-scale photometric [+ planar prior]) -> geometric-consistency iterations
 // [+ planar prior] -> fusion -> MPMVS_model.ply, on the same dense-folder layout and with the same output files.
 //
-//   mpmvs_main [config.yaml] [--seed N] [--tex f32|u8] [--no-fusion] [--gpu-fusion] [--resident [--in-flight N] [--device D] [--gpus G]] [--profile] [--check-inputs DIR] [--fusion-only]
+//   mpmvs_main [config.yaml] [--seed N] [--tex f32|u8] [--no-fusion] [--gpu-fusion] [--resident [--in-flight N] [--device D] [--gpus G]] [--profile] [--check-inputs DIR] [--fusion-only] [--arithmetic exact|fast]
 //
 // Default: the reference's strictly sequential order (one ProcessProblem at a time, results exchanged in place).
 // --resident: every view uploaded once into a per-GPU image cache, one resident handle per reference image, depth maps
@@ -575,6 +575,8 @@ int main(int argc, char* argv[]) {
         else if (!strcmp(argv[i], "--in-flight") && i + 1 < argc) in_flight = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--gpus") && i + 1 < argc) n_gpus = atoi(argv[++i]);
+        // both arithmetics are in the one library; every handle created from here on starts with this one (mpmvs_default_arithmetic)
+        else if (!strcmp(argv[i], "--arithmetic") && i + 1 < argc) setenv("MPMVS_ARITHMETIC", argv[++i], 1);
         else yaml = argv[i];
     }
     try {
@@ -586,8 +588,11 @@ int main(int argc, char* argv[]) {
             return 0;
         }
         std::cout << "Input data path:" << config.input_folder << "\nOutput data path:" << config.output_folder << std::endl;
-        std::cout << "Kernels: " << mpmvs_build_flavor() << " arithmetic"
-                  << (!strcmp(mpmvs_build_flavor(), "shipped") ? " (mpmvs_main_exact runs the build that is bit-identical to the reference's kernels)" : "")
+        std::cout << "Kernels: " << mpmvs_arithmetic_name(mpmvs_default_arithmetic()) << " arithmetic"
+                  << (mpmvs_default_arithmetic() == MPMVS_ARITH_EXACT
+                          ? (tex == MPMVS_TEX_F32 ? " (bit-identical to the reference's kernels; --arithmetic fast --tex u8 is faster, statistically equal)"
+                                                  : " on 8-bit views (the bilinear filter differs in the last bits: use --tex f32 for bit-identity)")
+                          : " (statistically equal to the reference's kernels; --arithmetic exact is bit-identical)")
                   << std::endl;
         mkdir(config.output_folder.c_str(), 0777);
         std::vector<Scene> Scenes;

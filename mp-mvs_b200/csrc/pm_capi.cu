@@ -17,6 +17,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <unordered_map>
@@ -89,9 +90,8 @@ struct mpmvs_problem {
     int2* d_vxy = nullptr; int3* d_tris = nullptr; pm_f4* d_tri_planes = nullptr; size_t vtx_cap = 0, tri_cap = 0;
     unsigned int* d_prior_count = nullptr;
     std::vector<short> h_cell_xy; std::vector<unsigned char> h_cell_n;
-#if PM_LITERAL_NCC == 2
+    int arith = MPMVS_ARITH_EXACT;     // which of the two compiled arithmetics the launches use (mpmvs_set_arithmetic)
     float lit_table[20];               // pm_literal_table evaluated on this device (mpmvs_create)
-#endif
 };
 
 namespace {
@@ -114,11 +114,9 @@ PmFrame make_frame(const mpmvs_problem* p) {
         if (p->cams[i].width != p->cache->W || p->cams[i].height != p->cache->H) soft = 1;
     F.soft_clamp = soft;
     F.tex = (unsigned long long)p->cache->tex;
-#if PM_LITERAL_NCC == 2
     for (int k = 0; k < 18; ++k) F.lit_sd[k / 6][k % 6] = p->lit_table[k];
     F.lit_rcp_spatial = p->lit_table[18];
     F.lit_rcp_color = p->lit_table[19];
-#endif
     return F;
 }
 
@@ -301,6 +299,7 @@ int enqueue_run(mpmvs_problem* p, uint64_t seed) {
     if (p->planar && !p->has_prior) return MPMVS_E_STATE;
     CK(cudaSetDevice(p->device));
     const PmFrame F = make_frame(p);
+    const PmLaunchers& L = pm_launchers(p->arith);
     PmState S = p->S;
     S.counters = nullptr;
     if (p->profiling & 2) {
@@ -322,13 +321,13 @@ int enqueue_run(mpmvs_problem* p, uint64_t seed) {
     CK(cudaEventRecord(p->ev0, p->stream));
     CK(mark());
     int launches = 0;
-    CK(pm_launch_init(F, S, p->dviews, seed, p->stream));
+    CK(L.init(F, S, p->dviews, seed, p->stream));
     CK(mark());
     ++launches;
     if (p->geom || p->planar) {
         for (int i = 0; i < p->max_iterations; ++i)
             for (int red = 0; red < 2; ++red) {
-                CK(pm_launch_sweep(F, S, p->dviews, red, i, 0, p->stream));
+                CK(L.sweep(F, S, p->dviews, red, i, 0, p->stream));
                 CK(mark());
                 ++launches;
             }
@@ -336,12 +335,12 @@ int enqueue_run(mpmvs_problem* p, uint64_t seed) {
         for (int s = p->max_scale; s >= 0; --s)
             for (int i = 0; i < p->max_iterations; ++i)
                 for (int red = 0; red < 2; ++red) {
-                    CK(pm_launch_sweep(F, S, p->dviews, red, i, s, p->stream));
+                    CK(L.sweep(F, S, p->dviews, red, i, s, p->stream));
                     CK(mark());
                     ++launches;
                 }
     }
-    CK(pm_launch_finalize(F, S, p->stream));
+    CK(L.finalize(F, S, p->stream));
     CK(mark());
     launches += 3;
     CK(cudaEventRecord(p->ev1, p->stream));
@@ -356,16 +355,28 @@ extern "C" {
 
 int mpmvs_version(void) { return 100; }
 
-const char* mpmvs_build_flavor(void) {
-#if PM_LITERAL_NCC == 2
-    return "literal2";
-#elif PM_LITERAL_NCC == 1
-    return "literal";
-#elif PM_LITERAL_WARP
-    return "litwarp";
-#else
-    return "shipped";
-#endif
+const char* mpmvs_build_flavor(void) { return "exact+fast"; }
+
+const char* mpmvs_arithmetic_name(int arithmetic) {
+    return arithmetic == MPMVS_ARITH_EXACT ? "exact" : (arithmetic == MPMVS_ARITH_FAST ? "fast" : "?");
+}
+
+int mpmvs_default_arithmetic(void) {
+    const char* e = getenv("MPMVS_ARITHMETIC");
+    if (e && (!strcmp(e, "fast") || !strcmp(e, "1"))) return MPMVS_ARITH_FAST;
+    return MPMVS_ARITH_EXACT;
+}
+
+int mpmvs_set_arithmetic(mpmvs_problem* p, int arithmetic) {
+    if (!p || (arithmetic != MPMVS_ARITH_EXACT && arithmetic != MPMVS_ARITH_FAST)) return MPMVS_E_ARG;
+    p->arith = arithmetic;
+    return MPMVS_OK;
+}
+
+int mpmvs_get_arithmetic(mpmvs_problem* p, int* arithmetic) {
+    if (!p || !arithmetic) return MPMVS_E_ARG;
+    *arithmetic = p->arith;
+    return MPMVS_OK;
 }
 
 const char* mpmvs_error_string(int code) {
@@ -396,8 +407,8 @@ int mpmvs_create(int device, void* stream, mpmvs_problem** out) {
     }
     cudaEventCreate(&p->ev0);
     cudaEventCreate(&p->ev1);
-#if PM_LITERAL_NCC == 2
-    {
+    p->arith = mpmvs_default_arithmetic();
+    {   // the constants of the exact arithmetic's bilateral weight as THIS device's MUFU unit evaluates them
         float* d = nullptr;
         cudaError_t e = cudaMalloc((void**)&d, sizeof(p->lit_table));
         if (e == cudaSuccess) e = pm_launch_literal_table(p->sigma_spatial, p->sigma_color, d, p->stream);
@@ -406,7 +417,6 @@ int mpmvs_create(int device, void* stream, mpmvs_problem** out) {
         cudaFree(d);
         if (e != cudaSuccess) { mpmvs_destroy(p); return (int)e; }
     }
-#endif
     *out = p;
     return MPMVS_OK;
 }
@@ -585,7 +595,10 @@ int mpmvs_set_src_depths(mpmvs_problem* p, const float* const* depth_host) {
         p->hviews[v].dw = sc.width; p->hviews[v].dh = sc.height; p->hviews[v].dpitch = sc.width;
     }
     p->has_depths = true;
-    return sync_frame_views(p);
+    int rc = sync_frame_views(p);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(p->stream));  // the caller may free or reuse its buffers on return (as in mpmvs_set_state)
+    return MPMVS_OK;
 }
 
 int mpmvs_set_src_depths_device(mpmvs_problem* p, const float* const* depth_dev, const size_t* pitch_bytes) {
@@ -758,7 +771,7 @@ int mpmvs_export_depth_device(mpmvs_problem* p, float* depth_dev, size_t pitch_b
 int mpmvs_init_only(mpmvs_problem* p, uint64_t seed) {
     if (!p || p->n < 2) return MPMVS_E_ARG;
     CK(cudaSetDevice(p->device));
-    CK(pm_launch_init(make_frame(p), p->S, p->dviews, seed, p->stream));
+    CK(pm_launchers(p->arith).init(make_frame(p), p->S, p->dviews, seed, p->stream));
     CK(cudaStreamSynchronize(p->stream));
     return MPMVS_OK;
 }
@@ -767,7 +780,7 @@ int mpmvs_half_sweep(mpmvs_problem* p, int red, int iter, int scale) {
     if (!p || p->n < 2) return MPMVS_E_ARG;
     if (p->geom && !p->has_depths) return MPMVS_E_STATE;
     CK(cudaSetDevice(p->device));
-    CK(pm_launch_sweep(make_frame(p), p->S, p->dviews, red ? 1 : 0, iter, scale, p->stream));
+    CK(pm_launchers(p->arith).sweep(make_frame(p), p->S, p->dviews, red ? 1 : 0, iter, scale, p->stream));
     CK(cudaStreamSynchronize(p->stream));
     return MPMVS_OK;
 }
@@ -775,7 +788,7 @@ int mpmvs_half_sweep(mpmvs_problem* p, int red, int iter, int scale) {
 int mpmvs_finalize(mpmvs_problem* p) {
     if (!p || p->n < 2) return MPMVS_E_ARG;
     CK(cudaSetDevice(p->device));
-    CK(pm_launch_finalize(make_frame(p), p->S, p->stream));
+    CK(pm_launchers(p->arith).finalize(make_frame(p), p->S, p->stream));
     CK(cudaStreamSynchronize(p->stream));
     return MPMVS_OK;
 }
@@ -815,7 +828,7 @@ int mpmvs_ncc_map(mpmvs_problem* p, const float* planes4_host, int scale, float*
     cudaError_t e = cudaMalloc((void**)&dout, out_bytes);
     if (e != cudaSuccess) { cudaFree(dp); return (int)e; }
     cudaMemcpyAsync(dp, planes4_host, p->wh * sizeof(pm_f4), cudaMemcpyHostToDevice, p->stream);
-    e = pm_launch_ncc_map(make_frame(p), p->dviews, dp, scale, dout, p->stream);
+    e = pm_launchers(p->arith).ncc_map(make_frame(p), p->dviews, dp, scale, dout, p->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, dout, out_bytes, cudaMemcpyDeviceToHost, p->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
     cudaFree(dp);
@@ -838,9 +851,9 @@ int mpmvs_ncc_bench(mpmvs_problem* p, const float* planes4_host, int scale, int 
     cudaMemsetAsync(dc, 0, sizeof(unsigned long long), p->stream);
     const PmFrame F = make_frame(p);
     // one counting pass (also warm-up), then the timed pass without the counter
-    e = pm_launch_ncc_bench(F, p->dviews, dp, scale, taps_per_side, n_views, reps, dout, dc, p->stream);
+    e = pm_launchers(p->arith).ncc_bench(F, p->dviews, dp, scale, taps_per_side, n_views, reps, dout, dc, p->stream);
     if (e == cudaSuccess) e = cudaEventRecord(p->ev0, p->stream);
-    if (e == cudaSuccess) e = pm_launch_ncc_bench(F, p->dviews, dp, scale, taps_per_side, n_views, reps, dout, nullptr, p->stream);
+    if (e == cudaSuccess) e = pm_launchers(p->arith).ncc_bench(F, p->dviews, dp, scale, taps_per_side, n_views, reps, dout, nullptr, p->stream);
     if (e == cudaSuccess) e = cudaEventRecord(p->ev1, p->stream);
     if (e == cudaSuccess) e = cudaEventSynchronize(p->ev1);
     if (e == cudaSuccess) e = cudaEventElapsedTime(ms, p->ev0, p->ev1);
@@ -862,7 +875,7 @@ int mpmvs_geom_map(mpmvs_problem* p, const float* planes4_host, float* out_host)
     cudaError_t e = cudaMalloc((void**)&dout, out_bytes);
     if (e != cudaSuccess) { cudaFree(dp); return (int)e; }
     cudaMemcpyAsync(dp, planes4_host, p->wh * sizeof(pm_f4), cudaMemcpyHostToDevice, p->stream);
-    e = pm_launch_geom_map(make_frame(p), p->dviews, dp, dout, p->stream);
+    e = pm_launchers(p->arith).geom_map(make_frame(p), p->dviews, dp, dout, p->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, dout, out_bytes, cudaMemcpyDeviceToHost, p->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
     cudaFree(dp);

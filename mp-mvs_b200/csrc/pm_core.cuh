@@ -1,11 +1,9 @@
 // pm_core.cuh -- per-pixel arithmetic of the PatchMatch path, written once for the sm_100a kernels.
 //
 // Behavioural spec: /root/reference/src/PatchMatch.cu ("cu:NNN" below). This is not a transcription:
-//   * the homography is evaluated in the hoisted form H = A_v + b_v m^T (per-view constants A_v, b_v
-//     prepared on the host; m = K_r^-T n / d per hypothesis), so a warped tap costs 5 FMA + 1 RCP instead
-//     of a 145-flop rebuild per NCC call (cu:228-288);
-//   * everything that depends only on (pixel, scale) -- bilateral weights' reference side, the weighted
-//     reference mean/variance -- is computed once per pixel per sweep, not once per (hypothesis, view);
+//   * everything that depends only on (pixel, scale) -- the 36 bilateral weights of the window, the weighted
+//     reference mean/variance -- is computed once per pixel per sweep (pm_ref_stats, weights kept in a per-thread
+//     shared-memory table), not once per (hypothesis, view) as the reference does (cu:355-414);
 //   * the reference window comes from a shared-memory tile (Ctx::ref), source samples from the texture
 //     unit (Ctx::src), source depths from plain global loads (Ctx::src_depth);
 //   * views with zero sampling weight are skipped where the reference multiplies their cost by 0
@@ -13,6 +11,18 @@
 //   * per-pixel scratch that the reference keeps in 1.5 KB of local arrays is reduced to the 8 x nsrc
 //     candidate cost table; view weights are 4-bit counters packed in two 64-bit registers.
 // All reference quirks that change results are kept and marked QUIRK.
+//
+// TWO ARITHMETICS, one library. The file is compiled twice into libmpmvs_b200.so (pm_kernels.cu with and without
+// -DPM_EXACT=1; everything below the types lives in a namespace named after the arithmetic, so the two sets of
+// kernels and launchers link side by side) and a handle picks one at run time (mpmvs_set_arithmetic):
+//   * exact (PM_EXACT=1, the default of the library): every floating-point operation of the reference's compiled
+//     kernels in the reference's order with the reference's roundings -- which products are fused into FMAs is written
+//     down explicitly (pm_rmul / pm_radd / pm_ffma), MUFU.RCP / MUFU.SQRT / MUFU.EX2 where its SASS has them. Results
+//     are BIT-IDENTICAL to the reference's kernels (tests/test_zz_fidelity_build_gpu.py). What is still hoisted is
+//     bit-safe: the reference-side sums, the weights (pure functions of the reference window), the relative pose
+//     R_s R_r^T, R_s (C_r - C_s) (hypothesis-invariant, formed once per problem by the same instructions);
+//   * fast (PM_EXACT=0): hoisted homography H = A_v + b_v m^T (per-view constants prepared on the host in double
+//     precision; a warped tap costs 5 FMA + 1 RCP), folded weight constants, rsqrt. Statistically equal results.
 //
 // The functions are templates over a context `Ctx` so that the very same code can be instantiated by
 // the test-only host emulation (tests/emul), which is how the logic is debugged without a GPU. The
@@ -39,35 +49,16 @@
 #ifndef PM_EARLY_OUT
 #define PM_EARLY_OUT 1   // stop scoring a refinement proposal once it can no longer be accepted (result-identical)
 #endif
-#ifndef PM_LITERAL_WARP
-// 1: warped tap coordinates in the reference's own operation order -- ComputeHomography per NCC call from the two
-// cameras (cu:228-279), ComputeCorrespondingPoint per tap on integer pixel positions (cu:281-288) -- instead of the
-// hoisted incremental form. Costs ~150 flop per NCC call and 3 FMA per tap; what it buys is source coordinates that are
-// bit-identical to the reference's, i.e. identical texture samples (a 1-ulp coordinate difference moves the unit's 8-bit
-// interpolation weights, which is most of the NCC difference to the reference). Experiment, off in
-// the shipped library; the expressions below are deliberately left to the compiler's own FMA contraction.
-#define PM_LITERAL_WARP 0
+#ifndef PM_WTAB
+#define PM_WTAB 1        // bilateral weights of a pixel's window: computed once per launch into a per-thread table (Ctx::wt)
+#endif                   // instead of once per tap of every NCC (result-identical: they depend on the reference window only)
+#ifndef PM_EXACT
+#define PM_EXACT 0
 #endif
-#ifndef PM_LITERAL_NCC
-// 1 (implies PM_LITERAL_WARP): the NCC sums as the reference forms them -- bilateral weight through sqrt / exp of the
-// run-time tap offsets (cu:318-323), per-row partial sums (cu:366-399), (w r) s products, variance and covariance in its
-// order, 1 - cov / sqrt(var var) (cu:400-413). On weak texture the variance is a difference of two numbers ~1e4 apart
-// from 1, so the last bit of every weight and the order of the additions are worth up to 1e-2 in cost: there the
-// difference to the reference comes from here, not from the coordinates (tests/tools/literal_ncc_check.py).
-// Still hoisted (bit-identical whether done once or per call): the reference-side sums and the centre pixel.
-// 2: the same arithmetic with the taps unrolled again. Level 1 gets the reference's FMA contraction by imitating its loop
-// structure and leaving the fusing to the compiler; level 2 writes down what the reference's SASS does -- every product it
-// rounds is pm_rmul, every fused multiply-add pm_ffma (device: __fmul_rn / __fmaf_rn, never re-fused; host: plain unfused
-// arithmetic, i.e. the oracle's) -- and takes the six spatial tap distances of a scale from a table the device computed
-// (MUFU.SQRT results, PmFrame::lit_sd) instead of folding them at compile time. Level 2 is the FIDELITY BUILD of the
-// library (`make exact`, variants/libmpmvs_b200_literal2.so): measured bit-identical to the reference's kernels on the
-// B200 -- every half-sweep, whole runs, the full-size run -- about 25 % slower than the shipped form
-// (profiles/r01_literal_variant.md; tests: test_emul_vs_oracle.py, test_sass_equivalence.py, test_zz_fidelity_build_gpu.py).
-#define PM_LITERAL_NCC 0
-#endif
-#if PM_LITERAL_NCC
-#undef PM_LITERAL_WARP
-#define PM_LITERAL_WARP 1
+#if PM_EXACT
+#define PM_ARITH_NS pm_exact
+#else
+#define PM_ARITH_NS pm_fast
 #endif
 #define PM_PI_F 3.14159265358979323846f
 // The reference multiplies by M_PI, a double literal: `perturbation * M_PI` (cu:671), `3 * perturbation * M_PI` (cu:559)
@@ -75,11 +66,13 @@
 // ulp below the float products 0.06283186 and 0.08726647. Compile-time constants either way.
 #define PM_PI_D 3.14159265358979323846
 
+#ifndef MPMVS_PM_TYPES
+#define MPMVS_PM_TYPES
 struct alignas(16) pm_f4 { float x, y, z, w; };
 
-// Per-source-view constants, prepared on the host in double precision (pm_capi.cu: build_view_consts).
+// Per-source-view constants (pm_views.h: pm_build_view_consts, host, double precision; Rrel / trel: pm_view_prep).
 struct PmView {
-    float A[9];   // K_s R_rel K_r^-1        (homography, cu:228-279 with n/d factored out)
+    float A[9];   // K_s R_rel K_r^-1        (fast arithmetic: homography, cu:228-279 with n/d factored out)
     float b[3];   // -K_s t_rel
     float w, h;   // source image size as float (bounds test of the warped centre, cu:351)
     float Mf[9];  // K_s R_s R_r^T K_r^-1     ref pixel (x,y,1)*z -> source homogeneous pixel (cu:582-615)
@@ -90,9 +83,10 @@ struct PmView {
     int dpitch;   // in floats
     int layer;    // layer of this view in the resident layered image texture
     const float* depth;        // source depth map (geom pass), linear device memory
-#if PM_LITERAL_WARP
+    // exact arithmetic (the layout is the same for both arithmetics of the library):
     float sK[9], sR[9], st[3], sC[3];   // the source camera as the reference holds it (struct Camera, PatchMatch.h:35-46)
-#endif
+    float Rrel[9], trel[3];             // R_s R_r^T and R_s (C_r - C_s) with the reference's roundings (cu:233-247), formed
+                                        // once per problem with the reference's instructions (pm_view_prep): hypothesis-invariant
 };
 
 // Reference-camera constants and run flags.
@@ -110,15 +104,14 @@ struct PmFrame {
     int soft_clamp;            // 1 when the views differ in size: clamp-to-edge is then done on the coordinates
     unsigned long long tex;    // cudaTextureObject_t of the layered image array (one handle, warp-uniform:
                                // a per-view handle makes the compiler serialise every fetch per unique handle)
-#if PM_LITERAL_WARP
+    // exact arithmetic:
     float K[9], t[3], C[3];    // the rest of the reference camera (R is above): ComputeHomography, BackProjectPoint2W, ProjectPoint
-    int one;                   // 1, as a run-time value: keeps the tap offsets of the literal weight out of constant folding
+    int one;                   // 1, as a run-time value (windows other than 6 x 6: keeps the tap offsets out of constant folding)
     float sigma_spatial, sigma_color;
-    // level 2: sqrt(i^2 + j^2) of the six tap classes at the three scales and the two reciprocals of the weight, as the
-    // DEVICE evaluates them under --use_fast_math (pm_literal_table; the host emulation fills in libm's values)
+    // sqrt(i^2 + j^2) of the six tap classes at the three scales and the two reciprocals of the weight, as the DEVICE
+    // evaluates them under --use_fast_math (pm_literal_table; the host emulation fills in libm's values)
     float lit_sd[3][6];
     float lit_rcp_spatial, lit_rcp_color;
-#endif
 };
 
 // Device-resident per-pixel state (SoA).
@@ -132,7 +125,9 @@ struct PmState {
     const uint32_t* mask;
     unsigned long long* counters;  // optional (profiling): [0] += NCC evaluations that ran their 36 taps
 };
+#endif  // MPMVS_PM_TYPES
 
+namespace PM_ARITH_NS {
 // ------------------------------------------------------------------------------------------------ math
 PM_HD float pm_ex2(float x) { return exp2f(x); }
 #if defined(__CUDA_ARCH__)
@@ -160,8 +155,8 @@ PM_HD void pm_count(unsigned long long* ctr, uint32_t n) {
 #endif
 }
 
-#if PM_LITERAL_NCC == 2
-// Pinned roundings (see PM_LITERAL_NCC): on the device exactly one instruction each, never contracted with a neighbour.
+#if PM_EXACT
+// Pinned roundings (exact arithmetic): on the device exactly one instruction each, never contracted with a neighbour.
 #if defined(__CUDA_ARCH__)
 PM_HD float pm_rmul(float a, float b) { return __fmul_rn(a, b); }
 PM_HD float pm_radd(float a, float b) { return __fadd_rn(a, b); }
@@ -173,6 +168,7 @@ __device__ __forceinline__ float pm_sqrt_approx(float x) { float y; asm("sqrt.ap
 PM_HD float pm_rmul(float a, float b) { return a * b; }
 PM_HD float pm_radd(float a, float b) { return a + b; }
 PM_HD float pm_ffma(float a, float b, float c) { return a * b + c; }   // the oracle is plain C: every product rounded
+#endif
 #endif
 // i^2 + j^2 of a tap in units of (step/2)^2 -> its class 0..5: 2, 10, 18, 26, 34, 50
 PM_HD constexpr int pm_tap_class(int u, int v) {
@@ -188,7 +184,6 @@ PM_HD void pm_literal_table(float one, float sigma_spatial, float sigma_color, f
     out20[18] = one / (2.0f * sigma_spatial * sigma_spatial);
     out20[19] = one / (2.0f * sigma_color * sigma_color);
 }
-#endif
 
 // ------------------------------------------------------------------------------------------------ RNG
 // XORWOW with cuRAND's start state for curand_init(seed, 0, 0) and curand_uniform's output map, so a
@@ -227,12 +222,41 @@ PM_HD void pm_rng_store(uint32_t* g, int idx, const PmRng& s) {
 // ------------------------------------------------------------------------------------------------ geometry
 PM_HD float pm_dot3(const pm_f4& a, const pm_f4& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 
-// ComputeDepthfromPlaneHypothesis, cu:84-87
-PM_HD float pm_depth_from_plane(const PmFrame& F, const pm_f4& pl, int x, int y) {
-    // K[0] / K[4] is formed on the device by the reference: under --use_fast_math an approximate division (x * rcp(x) is
-    // not always 1 when the two focal lengths are equal), so it is formed here and not on the host
+// ComputeDepthfromPlaneHypothesis, cu:84-87.
+// K[0] / K[4] is formed on the device by the reference: under --use_fast_math an approximate division (x * rcp(x) is
+// not always 1 when the two focal lengths are equal), so it is formed here and not on the host.
+//
+// Exact arithmetic: nvcc contracts the reference's three-term denominator in TWO ways depending on the inlined copy
+// (SASS of oracle/_ref, BlackPixelUpdate / RedPixelUpdate; tests/tools/sass_dag.py lists them):
+//   form 0, every copy but one:            FFMA(fx, nz, FFMA(nx, x - cx,  FMUL(ny, yt)))     yt = (fx * RCP(fy)) * (y - cy)
+//   form 1, ComputeGeomConsistencyCost's copy inside PlaneHypothesisRefinement (cu:687):
+//                                          FFMA(fx, nz, FFMA(ny, yt,      FMUL(x - cx, nx)))
+// and depth = FMUL(FMUL(fx, -w), RCP(den)); where the reference subtracts the prior's depth from a depth that has no
+// other use (cu:939-940; not cu:949-950, whose depth_now is the outer one) the last product is fused into the subtraction: FFMA(fx * -w, RCP(den), -depth_prior).
+// Left to the compiler, which copy gets which form follows OUR inlining, not the reference's -- so the device code pins
+// every operation. Host (emulation, tests only): the oracle's plain expression, where all forms coincide.
+#if PM_EXACT && defined(__CUDA_ARCH__)
+PM_HD float pm_depth_den(const PmFrame& F, const pm_f4& pl, int x, int y, int form) {
+    const float xt = __fadd_rn((float)x, -F.cx);
+    const float yt = __fmul_rn(__fmul_rn(F.fx, pm_rcp_approx(F.fy)), __fadd_rn((float)y, -F.cy));
+    const float inner = form ? __fmaf_rn(pl.y, yt, __fmul_rn(xt, pl.x)) : __fmaf_rn(pl.x, xt, __fmul_rn(pl.y, yt));
+    return __fmaf_rn(F.fx, pl.z, inner);
+}
+PM_HD float pm_depth_from_plane(const PmFrame& F, const pm_f4& pl, int x, int y, int form = 0) {
+    return __fmul_rn(__fmul_rn(F.fx, -pl.w), pm_rcp_approx(pm_depth_den(F, pl, x, y, form)));
+}
+PM_HD float pm_depth_minus(const PmFrame& F, const pm_f4& pl, int x, int y, float sub) {
+    return __fmaf_rn(__fmul_rn(F.fx, -pl.w), pm_rcp_approx(pm_depth_den(F, pl, x, y, 0)), -sub);
+}
+#else
+PM_HD float pm_depth_from_plane(const PmFrame& F, const pm_f4& pl, int x, int y, int form = 0) {
+    (void)form;
     return -pl.w * F.fx / ((x - F.cx) * pl.x + (F.fx / F.fy) * (y - F.cy) * pl.y + F.fx * pl.z);
 }
+PM_HD float pm_depth_minus(const PmFrame& F, const pm_f4& pl, int x, int y, float sub) {
+    return pm_depth_from_plane(F, pl, x, y) - sub;
+}
+#endif
 // GetPlane2Origin, cu:163-176
 PM_HD float pm_plane_distance(const PmFrame& F, int x, int y, float depth, const pm_f4& n) {
     const float X0 = depth * (x - F.cx) / F.fx, X1 = depth * (y - F.cy) / F.fy;
@@ -312,16 +336,14 @@ struct PmRefStats {
     float var_r;     // weighted variance of the reference patch
 };
 
-#if PM_LITERAL_NCC
-// ComputeBilateralWeight, cu:318-323. The offsets arrive as run-time values (the reference's loop counters are), so the
-// square root is the device's approximate one under --use_fast_math there and here, not a compile-time constant.
+#if PM_EXACT
+// ComputeBilateralWeight, cu:318-323, for windows other than the reference's 6 x 6 (NCC microbenchmark only): the offsets
+// arrive as run-time values, so the square root is the device's approximate one under --use_fast_math.
 PM_HD float pm_weight_literal(float x_dist, float y_dist, float pix, float center_pix, float sigma_spatial, float sigma_color) {
     const float spatial_dist = sqrtf(x_dist * x_dist + y_dist * y_dist);
     const float color_dist = fabsf(pix - center_pix);
     return expf(-spatial_dist / (2.0f * sigma_spatial * sigma_spatial) - color_dist / (2.0f * sigma_color * sigma_color));
 }
-#endif
-#if PM_LITERAL_NCC == 2
 // The same weight as the reference's SASS evaluates it (RefNccMap / BlackPixelUpdate in oracle/_ref):
 //   EX2(1.4426950216 * FFMA(-SQRT(i^2 + j^2), RCP(2 s_s s_s), -(|r - r0| * RCP(2 s_c s_c))))
 // with the square root and the reciprocals taken from the device-computed table. Host: the oracle's expression.
@@ -337,83 +359,67 @@ PM_HD float pm_weight_pinned(const PmFrame& F, int cls, float r, float r0) {
 }
 #endif
 
+// The bilateral weight of tap (a, b) of the window (cu:318-323): a pure function of the reference window.
+template <int SCALE, int TAPS>
+PM_HD float pm_tap_weight(const PmFrame& F, int a, int b, float r, float r0) {
+    constexpr int HS = 1 << SCALE;
+    const int u = 2 * a - (TAPS - 1), v = 2 * b - (TAPS - 1);
+#if PM_EXACT
+    // the table holds the reference's 6 x 6 window; other windows (NCC microbenchmark only) take the square root at run time
+    return TAPS == 6 ? pm_weight_pinned<SCALE>(F, pm_tap_class(u, v), r, r0)
+                     : pm_weight_literal((float)(u * HS * F.one), (float)(v * HS * F.one), r, r0, F.sigma_spatial, F.sigma_color);
+#else
+    return pm_ex2(fmaf(fabsf(r - r0), -F.col_k, (HS * pm_tap_dist_n<TAPS>(u, v)) * F.spat_k));
+#endif
+}
+
+// Reference side of ComputeBilateralNCC for one pixel: the TAPS x TAPS weights go to the thread's table c.wt(a * TAPS + b)
+// (every NCC of this pixel in this launch reads them back: 14 x (N-1) times in a half-sweep), the weighted sums to PmRefStats.
 template <int SCALE, class Ctx, int TAPS = 6>
 PM_HD PmRefStats pm_ref_stats(const Ctx& c, const PmFrame& F) {
     constexpr int HS = 1 << SCALE;  // step/2: taps at (2a-5)*HS
     PmRefStats st;
     st.r0 = c.ref(0, 0);
-#if PM_LITERAL_NCC == 2
-    {   // reference-side half of cu:355-405 with pinned roundings: FMUL r*w, FADD sum w, FFMA(r, r*w, .), FADD sum r*w per
-        // tap, rows added with FADD; 1/sum through MUFU.RCP, mean by FMUL, variance FFMA(sum rr, inv, -mean^2)
-        float sum_ref = 0.0f, sum_ref_ref = 0.0f, weight_sum = 0.0f;
+#if PM_EXACT
+    // reference-side half of cu:355-405 with pinned roundings: FMUL r*w, FADD sum w, FFMA(r, r*w, .), FADD sum r*w per
+    // tap, rows added with FADD; 1/sum through MUFU.RCP, mean by FMUL, variance FFMA(sum rr, inv, -mean^2)
+    float sum_ref = 0.0f, sum_ref_ref = 0.0f, weight_sum = 0.0f;
 #pragma unroll
-        for (int a = 0; a < TAPS; ++a) {
-            const int i = (2 * a - (TAPS - 1)) * HS;
-            float row_ref = 0.0f, row_ref_ref = 0.0f, row_weight = 0.0f;
+    for (int a = 0; a < TAPS; ++a) {
+        const int i = (2 * a - (TAPS - 1)) * HS;
+        float row_ref = 0.0f, row_ref_ref = 0.0f, row_weight = 0.0f;
 #pragma unroll
-            for (int b = 0; b < TAPS; ++b) {
-                const int j = (2 * b - (TAPS - 1)) * HS;
-                const float r = c.ref(i, j);
-                // the table holds the reference's 6 x 6 window; other windows (NCC microbenchmark only) take the square root at run time
-                const float w = TAPS == 6 ? pm_weight_pinned<SCALE>(F, pm_tap_class(2 * a - (TAPS - 1), 2 * b - (TAPS - 1)), r, st.r0)
-                                          : pm_weight_literal((float)(i * F.one), (float)(j * F.one), r, st.r0, F.sigma_spatial, F.sigma_color);
-                const float rw = pm_rmul(w, r);
-                row_ref = pm_radd(row_ref, rw);
-                row_ref_ref = pm_ffma(rw, r, row_ref_ref);
-                row_weight = pm_radd(row_weight, w);
-            }
-            sum_ref = pm_radd(sum_ref, row_ref);
-            sum_ref_ref = pm_radd(sum_ref_ref, row_ref_ref);
-            weight_sum = pm_radd(weight_sum, row_weight);
+        for (int b = 0; b < TAPS; ++b) {
+            const int j = (2 * b - (TAPS - 1)) * HS;
+            const float r = c.ref(i, j);
+            const float w = pm_tap_weight<SCALE, TAPS>(F, a, b, r, st.r0);
+            if (PM_WTAB) c.wt(a * TAPS + b) = w;
+            const float rw = pm_rmul(w, r);
+            row_ref = pm_radd(row_ref, rw);
+            row_ref_ref = pm_ffma(rw, r, row_ref_ref);
+            row_weight = pm_radd(row_weight, w);
         }
-        st.inv_sw = 1.0f / weight_sum;
-        st.mean_r = pm_rmul(sum_ref, st.inv_sw);
+        sum_ref = pm_radd(sum_ref, row_ref);
+        sum_ref_ref = pm_radd(sum_ref_ref, row_ref_ref);
+        weight_sum = pm_radd(weight_sum, row_weight);
+    }
+    st.inv_sw = 1.0f / weight_sum;
+    st.mean_r = pm_rmul(sum_ref, st.inv_sw);
 #if defined(__CUDA_ARCH__)
-        st.var_r = __fmaf_rn(sum_ref_ref, st.inv_sw, -__fmul_rn(st.mean_r, st.mean_r));
+    st.var_r = __fmaf_rn(sum_ref_ref, st.inv_sw, -__fmul_rn(st.mean_r, st.mean_r));
 #else
-        sum_ref_ref *= st.inv_sw;
-        st.var_r = sum_ref_ref - st.mean_r * st.mean_r;
+    sum_ref_ref *= st.inv_sw;
+    st.var_r = sum_ref_ref - st.mean_r * st.mean_r;
 #endif
-        return st;
-    }
-#elif PM_LITERAL_NCC
-    {   // the reference-side half of cu:355-405: rows of the window are summed on their own, then added up
-        // run-time loop bounds, not unrolled: the reference's loops are (cu:340-346,365,373), and the compiler's choice of
-        // which products to fuse into FMAs follows the loop structure (unrolled taps get their spatial term hoisted and
-        // the colour term fused; the reference's SASS rounds the colour term and fuses the spatial one)
-        const int step = 2 * HS * F.one, radius = (TAPS - 1) * step / 2;
-        float sum_ref = 0.0f, sum_ref_ref = 0.0f, weight_sum = 0.0f;
-#pragma unroll 1
-        for (int i = -radius; i < radius + 1; i += step) {
-            float row_ref = 0.0f, row_ref_ref = 0.0f, row_weight = 0.0f;
-#pragma unroll 1
-            for (int j = -radius; j < radius + 1; j += step) {
-                const float r = c.ref(i, j);
-                const float w = pm_weight_literal(i, j, r, st.r0, F.sigma_spatial, F.sigma_color);
-                row_ref += w * r;
-                row_ref_ref += w * r * r;
-                row_weight += w;
-            }
-            sum_ref += row_ref;
-            sum_ref_ref += row_ref_ref;
-            weight_sum += row_weight;
-        }
-        st.inv_sw = 1.0f / weight_sum;
-        sum_ref *= st.inv_sw;
-        sum_ref_ref *= st.inv_sw;
-        st.mean_r = sum_ref;
-        st.var_r = sum_ref_ref - sum_ref * sum_ref;
-        return st;
-    }
-#endif
+#else
     float sw = 0.f, swr = 0.f, swrr = 0.f;
 #pragma unroll
     for (int a = 0; a < TAPS; ++a) {
 #pragma unroll
         for (int b = 0; b < TAPS; ++b) {
-            const int u = 2 * a - (TAPS - 1), v = 2 * b - (TAPS - 1);
-            const float r = c.ref(u * HS, v * HS);
-            const float w = pm_ex2(fmaf(fabsf(r - st.r0), -F.col_k, (HS * pm_tap_dist_n<TAPS>(u, v)) * F.spat_k));
+            const float r = c.ref((2 * a - (TAPS - 1)) * HS, (2 * b - (TAPS - 1)) * HS);
+            const float w = pm_tap_weight<SCALE, TAPS>(F, a, b, r, st.r0);
+            if (PM_WTAB) c.wt(a * TAPS + b) = w;
             sw += w;
             swr = fmaf(w, r, swr);
             swrr = fmaf(w * r, r, swrr);
@@ -422,48 +428,47 @@ PM_HD PmRefStats pm_ref_stats(const Ctx& c, const PmFrame& F) {
     st.inv_sw = 1.0f / sw;
     st.mean_r = swr * st.inv_sw;
     st.var_r = swrr * st.inv_sw - st.mean_r * st.mean_r;
+#endif
     return st;
 }
 
-// Per-hypothesis part of the homography: m = K_r^-T n / d, q0 = m . (x, y, 1)  (= -1/z at the pixel).
+// Per-hypothesis part of the homography. fast: m = K_r^-T n / d, q0 = m . (x, y, 1)  (= -1/z at the pixel);
+// exact: the plane itself (the reference rebuilds H from it per view, cu:228-279).
 struct PmHyp {
-    float mx, my, q0;
-#if PM_LITERAL_WARP
+#if PM_EXACT
     pm_f4 pl;
+#else
+    float mx, my, q0;
 #endif
 };
 PM_HD PmHyp pm_hyp(const PmFrame& F, const pm_f4& pl, int x, int y) {
-    const float id = 1.0f / pl.w;
     PmHyp h;
-#if PM_LITERAL_WARP
+#if PM_EXACT
+    (void)F; (void)x; (void)y;
     h.pl = pl;
-#endif
+#else
+    const float id = 1.0f / pl.w;
     h.mx = pl.x * F.ifx * id;
     h.my = pl.y * F.ify * id;
     const float mz = (pl.z - pl.x * F.cx * F.ifx - pl.y * F.cy * F.ify) * id;
     h.q0 = fmaf(h.mx, (float)x, fmaf(h.my, (float)y, mz));
+#endif
     return h;
 }
 
-#if PM_LITERAL_WARP
-// ComputeHomography, cu:228-279, operation by operation (relative pose, plane term, K_r^-1 with zero skew, the part of
-// K_s it uses); plain expressions, so nvcc contracts them the way it contracts the reference's.
+#if PM_EXACT
+// ComputeHomography, cu:228-279. Its hypothesis-invariant head -- R_relative = R_s R_r^T and t_relative = R_s (C_r - C_s),
+// cu:233-247 -- is formed once per problem with the reference's roundings (pm_views.h: pm_view_prep) and arrives as
+// PmView::Rrel / trel; the rest, cu:248-279, follows operation by operation (plane term, K_r^-1 with zero skew, the part
+// of K_s it uses): plain expressions, so nvcc contracts them the way it contracts the reference's (checked on the SASS by
+// tests/test_sass_equivalence.py).
 PM_HD void pm_homography_literal(const PmFrame& F, const PmView& V, const pm_f4& pl, float* H) {
-    float Rrel[9], trel[3], tmp[9];
+    float tmp[9];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-#pragma unroll
-        for (int b = 0; b < 3; ++b)
-            Rrel[3 * a + b] = V.sR[3 * a] * F.R[3 * b] + V.sR[3 * a + 1] * F.R[3 * b + 1] + V.sR[3 * a + 2] * F.R[3 * b + 2];
-    }
-    const float c0 = F.C[0] - V.sC[0], c1 = F.C[1] - V.sC[1], c2 = F.C[2] - V.sC[2];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) trel[a] = V.sR[3 * a] * c0 + V.sR[3 * a + 1] * c1 + V.sR[3 * a + 2] * c2;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        H[3 * a] = Rrel[3 * a] - trel[a] * pl.x / pl.w;
-        H[3 * a + 1] = Rrel[3 * a + 1] - trel[a] * pl.y / pl.w;
-        H[3 * a + 2] = Rrel[3 * a + 2] - trel[a] * pl.z / pl.w;
+        H[3 * a] = V.Rrel[3 * a] - V.trel[a] * pl.x / pl.w;
+        H[3 * a + 1] = V.Rrel[3 * a + 1] - V.trel[a] * pl.y / pl.w;
+        H[3 * a + 2] = V.Rrel[3 * a + 2] - V.trel[a] * pl.z / pl.w;
     }
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -494,7 +499,7 @@ PM_HD float pm_ncc(const Ctx& c, const PmFrame& F, const PmRefStats& st, int v, 
                    uint32_t& nexec) {
     constexpr int HS = 1 << SCALE;
     const PmView& V = c.view(v);
-#if PM_LITERAL_WARP
+#if PM_EXACT
     float Hm[9];
     pm_homography_literal(F, V, hyp.pl, Hm);
     float pcx, pcy;
@@ -502,7 +507,6 @@ PM_HD float pm_ncc(const Ctx& c, const PmFrame& F, const PmRefStats& st, int v, 
     if (pcx >= V.w || pcx < 0.0f || pcy >= V.h || pcy < 0.0f) return 2.0f;  // cu:351-353
     if (st.var_r < 1e-5f) return 2.0f;                                     // cu:407 (hypothesis-invariant)
     ++nexec;
-#if PM_LITERAL_NCC == 2
     // source-side half of cu:355-413 as the reference's SASS evaluates it, taps unrolled. Per row: FMUL H0 px, H3 px, H6 px.
     // Per tap: numerators FADD(H2, FFMA(H1, py, H0 px)), ...; MUFU.RCP(Z); coordinates FFMA(X, rcp, 0.5); FMUL r*w, FMUL s*w,
     // FADD sum(w s), FFMA(s, s*w, .), FFMA(s, r*w, .). Host: the oracle's divisions and unfused products, same order.
@@ -527,8 +531,7 @@ PM_HD float pm_ncc(const Ctx& c, const PmFrame& F, const PmRefStats& st, int v, 
             const float s = c.src(v, X / Z + 0.5f, Y / Z + 0.5f);
 #endif
             const float r = c.ref(i, j);
-            const float w = TAPS == 6 ? pm_weight_pinned<SCALE>(F, pm_tap_class(2 * a - (TAPS - 1), 2 * b - (TAPS - 1)), r, st.r0)
-                                      : pm_weight_literal((float)(i * F.one), (float)(j * F.one), r, st.r0, F.sigma_spatial, F.sigma_color);
+            const float w = PM_WTAB ? c.wt(a * TAPS + b) : pm_tap_weight<SCALE, TAPS>(F, a, b, r, st.r0);
             const float sw = pm_rmul(w, s), rw = pm_rmul(w, r);
             row_src = pm_radd(row_src, sw);
             row_src_src = pm_ffma(sw, s, row_src_src);
@@ -553,65 +556,6 @@ PM_HD float pm_ncc(const Ctx& c, const PmFrame& F, const PmRefStats& st, int v, 
     if (var_src < 1e-5f) return 2.0f;
     const float covar_src_ref = sum_ref_src - st.mean_r * sum_src;
     return fmaxf(0.0f, fminf(2.0f, 1.0f - covar_src_ref / sqrtf(st.var_r * var_src)));
-#endif
-#elif PM_LITERAL_NCC
-    // source-side half of cu:355-413
-    const int step = 2 * HS * F.one, radius = (TAPS - 1) * step / 2;     // run-time bounds: see pm_ref_stats
-    float sum_src = 0.0f, sum_src_src = 0.0f, sum_ref_src = 0.0f;
-#pragma unroll 1
-    for (int i = -radius; i < radius + 1; i += step) {
-        float row_src = 0.0f, row_src_src = 0.0f, row_ref_src = 0.0f;
-#pragma unroll 1
-        for (int j = -radius; j < radius + 1; j += step) {
-            const float r = c.ref(i, j);
-            float sx, sy;
-            pm_warp_literal(Hm, x + i, y + j, sx, sy);
-            const float s = c.src(v, sx + 0.5f, sy + 0.5f);
-            const float w = pm_weight_literal(i, j, r, st.r0, F.sigma_spatial, F.sigma_color);
-            row_src += w * s;
-            row_src_src += w * s * s;
-            row_ref_src += w * r * s;
-        }
-        sum_src += row_src;
-        sum_src_src += row_src_src;
-        sum_ref_src += row_ref_src;
-    }
-    sum_src *= st.inv_sw;
-    sum_src_src *= st.inv_sw;
-    const float var_src = sum_src_src - sum_src * sum_src;
-#if defined(__CUDA_ARCH__)
-    // The reference scales sum_ref_src before its variance test, so its compiled covariance is FFMA(-mean_r, mean_s,
-    // round(sum_ref_src * inv)) (SASS of oracle/_ref, RefNccMap / BlackPixelUpdate); left to itself the compiler fuses the
-    // other product here because the scaling can sink below the early return. Pinned explicitly.
-    sum_ref_src = __fmul_rn(sum_ref_src, st.inv_sw);
-    if (var_src < 1e-5f) return 2.0f;
-    const float covar_src_ref = __fmaf_rn(-st.mean_r, sum_src, sum_ref_src);
-#else
-    sum_ref_src *= st.inv_sw;
-    if (var_src < 1e-5f) return 2.0f;
-    const float covar_src_ref = sum_ref_src - st.mean_r * sum_src;
-#endif
-    const float var_ref_src = sqrtf(st.var_r * var_src);
-    return fmaxf(0.0f, fminf(2.0f, 1.0f - covar_src_ref / var_ref_src));
-#else
-    float s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-    for (int a = 0; a < TAPS; ++a) {
-        const int i = (2 * a - (TAPS - 1)) * HS;
-#pragma unroll
-        for (int b = 0; b < TAPS; ++b) {
-            const int j = (2 * b - (TAPS - 1)) * HS;
-            float sx, sy;
-            pm_warp_literal(Hm, x + i, y + j, sx, sy);
-            const float s = c.src(v, sx + 0.5f, sy + 0.5f);
-            const float r = c.ref(i, j);
-            const float w = pm_ex2(fmaf(fabsf(r - st.r0), -F.col_k, (HS * pm_tap_dist_n<TAPS>(2 * a - (TAPS - 1), 2 * b - (TAPS - 1))) * F.spat_k));
-            const float ws = w * s;
-            s1 += ws;
-            s2 = fmaf(ws, s, s2);
-            s3 = fmaf(ws, r, s3);
-        }
-    }
 #endif
 #else
     const float fxp = (float)x, fyp = (float)y;
@@ -640,15 +584,12 @@ PM_HD float pm_ncc(const Ctx& c, const PmFrame& F, const PmRefStats& st, int v, 
             const float ys = fmaf(fmaf((float)j, Vy, Ya), rz, 0.5f);
             const float s = c.src(v, xs, ys);
             const float r = c.ref(i, j);
-            const float w = pm_ex2(fmaf(fabsf(r - st.r0), -F.col_k, (HS * pm_tap_dist_n<TAPS>(2 * a - (TAPS - 1), 2 * b - (TAPS - 1))) * F.spat_k));
-            const float ws = w * s;
+            const float ws = (PM_WTAB ? c.wt(a * TAPS + b) : pm_tap_weight<SCALE, TAPS>(F, a, b, r, st.r0)) * s;
             s1 += ws;
             s2 = fmaf(ws, s, s2);
             s3 = fmaf(ws, r, s3);
         }
     }
-#endif
-#if !PM_LITERAL_NCC
     const float mean_s = s1 * st.inv_sw;
     const float var_s = s2 * st.inv_sw - mean_s * mean_s;
     if (var_s < 1e-5f) return 2.0f;
@@ -657,8 +598,8 @@ PM_HD float pm_ncc(const Ctx& c, const PmFrame& F, const PmRefStats& st, int v, 
 #endif
 }
 
-// ComputeGeomConsistencyCost, cu:617-640, with the four camera transforms pre-multiplied per view.
-#if PM_LITERAL_NCC
+// ComputeGeomConsistencyCost, cu:617-640.
+#if PM_EXACT
 // BackProjectPoint2W, cu:582-603, and ProjectPoint, cu:605-615, on a camera given as (K, R, t, C)
 PM_HD void pm_backproject_literal(float x, float y, float depth, const float* K, const float* R, const float* C, float* X) {
     const float px = depth * (x - K[2]) / K[0];
@@ -681,24 +622,26 @@ PM_HD void pm_project_literal(const float* X, const float* K, const float* R, co
 }
 #endif
 
+// depth_form: which contraction of the depth denominator the reference's inlined copy has (pm_depth_from_plane)
 template <class Ctx>
-PM_HD float pm_geom_cost(const Ctx& c, const PmFrame& F, int v, const pm_f4& pl, int x, int y) {
+PM_HD float pm_geom_cost(const Ctx& c, const PmFrame& F, int v, const pm_f4& pl, int x, int y, int depth_form = 0) {
     const PmView& V = c.view(v);
-#if PM_LITERAL_NCC
-    {   // cu:617-640 through the two cameras, not through the pre-multiplied per-view transforms
-        const float depth = pm_depth_from_plane(F, pl, x, y);
-        float P3[3], sx, sy;
-        pm_backproject_literal((float)x, (float)y, depth, F.K, F.R, F.C, P3);
-        pm_project_literal(P3, V.sK, V.sR, V.st, sx, sy);
-        const float sd = c.src_depth(v, pm_f2i(sx), pm_f2i(sy));
-        if (sd == 0.0f) return 3.0f;
-        float Q3[3], bx, by;
-        pm_backproject_literal(sx, sy, sd, V.sK, V.sR, V.sC, Q3);
-        pm_project_literal(Q3, F.K, F.R, F.t, bx, by);
-        const float diff_col = x - bx, diff_row = y - by;
-        return fminf(3.0f, sqrtf(diff_col * diff_col + diff_row * diff_row));
-    }
-#endif
+#if PM_EXACT
+    // cu:617-640 through the two cameras, not through the pre-multiplied per-view transforms
+    const float depth = pm_depth_from_plane(F, pl, x, y, depth_form);
+    float P3[3], sx, sy;
+    pm_backproject_literal((float)x, (float)y, depth, F.K, F.R, F.C, P3);
+    pm_project_literal(P3, V.sK, V.sR, V.st, sx, sy);
+    const float sd = c.src_depth(v, pm_f2i(sx), pm_f2i(sy));
+    if (sd == 0.0f) return 3.0f;
+    float Q3[3], bx, by;
+    pm_backproject_literal(sx, sy, sd, V.sK, V.sR, V.sC, Q3);
+    pm_project_literal(Q3, F.K, F.R, F.t, bx, by);
+    const float diff_col = x - bx, diff_row = y - by;
+    return fminf(3.0f, sqrtf(diff_col * diff_col + diff_row * diff_row));
+#else
+    // the four camera transforms pre-multiplied per view
+    (void)depth_form;
     const float z = pm_depth_from_plane(F, pl, x, y);
     const float fxp = (float)x, fyp = (float)y;
     const float hx = fmaf(z, fmaf(V.Mf[0], fxp, fmaf(V.Mf[1], fyp, V.Mf[2])), V.vf[0]);
@@ -712,6 +655,7 @@ PM_HD float pm_geom_cost(const Ctx& c, const PmFrame& F, int v, const pm_f4& pl,
     const float bz = fmaf(sd, fmaf(V.Mb[6], sx, fmaf(V.Mb[7], sy, V.Mb[8])), V.vb[2]);
     const float dc = fxp - bx / bz, dr = fyp - by / bz;
     return fminf(3.0f, sqrtf(dc * dc + dr * dr));
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ view weights
@@ -917,14 +861,14 @@ PM_HD void pm_sweep_pixel(const Ctx& c, const PmFrame& F, const PmState& S, int 
                         pm_f4 pl = cur;
                         if ((flags >> r) & 1u) {
                             pl = S.planes[pos[r]];
-                            const float dd = pm_depth_from_plane(F, pl, x, y) - dprior;
+                            const float dd = pm_depth_minus(F, pl, x, y, dprior);
                             const float ad = acosf(pm_dot3(pp, pl));
                             const float prior = 0.5f + pm_exp(-dd * dd / two_ds2) * pm_exp(-ad * ad / two_as2);
                             rf = pm_exp(-fc[r] * fc[r] / 0.18f) * prior;
                         }
                         if (r == 0 || rf >= rbest) { rbest = rf; kmax = r; cand_best = pl; }
                     }
-                    const float dd = depth_now - dprior;
+                    const float dd = depth_now - dprior;   // cu:949-950: the local depth_now is the outer one (CSE): plain FADD
                     const float ad = acosf(pm_dot3(pp, cur));
                     const float prior = 0.5f + pm_exp(-dd * dd / two_ds2) * pm_exp(-ad * ad / two_as2);
                     const float rc_now = pm_exp(-cost_now * cost_now / 0.18f) * prior;
@@ -1020,7 +964,7 @@ PM_HD void pm_sweep_pixel(const Ctx& c, const PmFrame& F, const PmState& S, int 
             } else {
                 const float wv = (float)vw.get(v);
                 if (F.geom) {
-                    const float g = 0.2f * pm_geom_cost(c, F, v, tp, x, y);
+                    const float g = 0.2f * pm_geom_cost(c, F, v, tp, x, y, h > 8);
                     tc += wv * (cst + g);
                     // QUIRK cu:689: in refinement the geometric part is weighted by view_weights[hypothesis index]
                     tg += (h == 8 ? wv : (float)vw.get(h - 9)) * g;
@@ -1138,5 +1082,8 @@ PM_HD float pm_median_depth(const pm_f4* planes, const float* costs, int W, int 
     const int m = n / 2;
     return (n % 2 == 0) ? (f[m - 1] + f[m]) / 2 : f[m];
 }
+
+}  // namespace PM_ARITH_NS
+using namespace PM_ARITH_NS;
 
 #endif  // MPMVS_PM_CORE_CUH

@@ -12,8 +12,15 @@
 // colour in a 32 x 8 pixel tile; the reference-image window of the tile (tile + 5*2^S halo) is staged once in
 // shared memory through the texture unit (exact texel fetch, hardware clamp-to-edge at the borders),
 // the per-view constants sit next to it. Source samples go through the texture unit: they are
-// homography-warped scattered bilinear reads, which is what the unit is built for, and it keeps the
-// reference's 9-bit-weight filtering bit-for-bit.
+// homography-warped scattered bilinear reads, which is what the unit is built for, and its filter is not
+// reproducible in software bit for bit (tools/tex_model_check.cu, profiles/r02_tex_model_check.json).
+//
+// Dynamic shared memory of a block: [nsrc x PmView][reference tile][36 bilateral weights x threads][8 x nsrc candidate
+// costs x threads (sweep only)]; the two per-thread tables are laid out [entry][thread] (conflict-free).
+//
+// This file is compiled TWICE into the library: as is (namespace pm_fast) and with -DPM_EXACT=1 (namespace pm_exact, the
+// reference's arithmetic bit for bit; pm_core.cuh). The helper kernels that do no arithmetic of the path (format
+// conversion, depth export, the RNG stream hook, the device-evaluated constant table) exist once, in the exact build.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -22,7 +29,7 @@
 #include "pm_core.cuh"
 #include "pm_kernels.h"
 
-namespace {
+namespace PM_ARITH_NS {   // pm_exact or pm_fast: the kernels of the two arithmetics carry the name in their symbols
 
 // Tuning knobs (compile-time; the defaults are what the B200 measurements in profiles/ selected).
 #ifndef PM_BH
@@ -47,6 +54,8 @@ struct Tile {
     static constexpr int FLOATS = PITCH * TH;
 };
 
+constexpr int WT_FLOATS = PM_WTAB ? 36 * BW * BH : 0;   // bilateral weights of the 6 x 6 window, per thread
+
 // candidate cost table of one thread in shared memory (stride = threads per block; PmTableLocal is the local-memory one)
 struct TableShared {
     float* p; int nsrc;   // p already offset by the thread index; element k at p[k * threads]
@@ -56,10 +65,12 @@ struct TableShared {
 template <int PITCH, bool SOFT_CLAMP, bool SCALED = false>
 struct DevCtx {
     const float* centre;   // shared-memory address of this thread's pixel inside the tile
+    float* wtab;           // this thread's column of the weight table (shared memory, stride = threads per block)
     const PmView* views;   // shared memory
     cudaTextureObject_t tex;
     float scale;           // texel value scale (255 for 8-bit UNORM storage); only read when SCALED
     __device__ __forceinline__ float ref(int dx, int dy) const { return centre[dy * PITCH + dx]; }
+    __device__ __forceinline__ float& wt(int k) const { return wtab[k * (BW * BH)]; }
     __device__ __forceinline__ float src(int v, float xs, float ys) const {
         const PmView& V = views[v];
         if (SOFT_CLAMP) {  // views smaller than the layered array: hardware clamp would hit the padding
@@ -77,6 +88,8 @@ struct DevCtx {
     }
     __device__ __forceinline__ const PmView& view(int v) const { return views[v]; }
 };
+
+__host__ __device__ __forceinline__ size_t views_bytes(int nsrc) { return ((size_t)nsrc * sizeof(PmView) + 15) & ~(size_t)15; }
 
 // cooperative staging: per-view constants, then the reference window of the tile whose top-left pixel is (x0, y0)
 template <int SCALE, int ROWS>
@@ -108,7 +121,7 @@ __global__ void __launch_bounds__(BW* BH, MIN_BLOCKS) pm_sweep_kernel(const PmFr
     using T = Tile<SCALE, 2 * BH>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PmView* sviews = reinterpret_cast<PmView*>(smem_raw);
-    float* tile = reinterpret_cast<float*>(smem_raw + PM_MAX_SRC * sizeof(PmView));
+    float* tile = reinterpret_cast<float*>(smem_raw + views_bytes(F.nsrc));
     const int x0 = blockIdx.x * BW, y0 = blockIdx.y * 2 * BH;
     stage_tile<SCALE, 2 * BH>(tile, sviews, gviews, F, x0, y0);
     const int tx = threadIdx.x, ly = 2 * threadIdx.y + ((tx & 1) ^ red);
@@ -116,11 +129,12 @@ __global__ void __launch_bounds__(BW* BH, MIN_BLOCKS) pm_sweep_kernel(const PmFr
     if (x >= F.W || y >= F.H) return;
     DevCtx<T::PITCH, CL, SC> c;
     c.centre = tile + (ly + T::R) * T::PITCH + (tx + T::R);
+    c.wtab = tile + T::FLOATS + threadIdx.y * BW + tx;
     c.views = sviews;
     c.tex = (cudaTextureObject_t)F.tex;
     c.scale = F.tex_scale;
 #if PM_CA_SMEM
-    float* cab = tile + T::FLOATS + threadIdx.y * BW + tx;
+    float* cab = c.wtab + WT_FLOATS;
     pm_sweep_pixel<SCALE>(c, F, S, x, y, iter, TableShared{cab, F.nsrc});
 #else
     float ca[8 * PM_MAX_SRC];
@@ -134,13 +148,14 @@ __global__ void __launch_bounds__(BW* BH, MIN_BLOCKS) pm_init_kernel(const PmFra
     using T = Tile<SCALE, BH>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PmView* sviews = reinterpret_cast<PmView*>(smem_raw);
-    float* tile = reinterpret_cast<float*>(smem_raw + PM_MAX_SRC * sizeof(PmView));
+    float* tile = reinterpret_cast<float*>(smem_raw + views_bytes(F.nsrc));
     const int x0 = blockIdx.x * BW, y0 = blockIdx.y * BH;
     stage_tile<SCALE, BH>(tile, sviews, gviews, F, x0, y0);
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     if (x >= F.W || y >= F.H) return;
     DevCtx<T::PITCH, CL, SC> c;
     c.centre = tile + (threadIdx.y + T::R) * T::PITCH + (threadIdx.x + T::R);
+    c.wtab = tile + T::FLOATS + threadIdx.y * BW + threadIdx.x;
     c.views = sviews;
     c.tex = (cudaTextureObject_t)F.tex;
     c.scale = F.tex_scale;
@@ -153,13 +168,14 @@ __global__ void __launch_bounds__(BW* BH, MIN_BLOCKS) pm_ncc_map_kernel(const Pm
     using T = Tile<SCALE, BH>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PmView* sviews = reinterpret_cast<PmView*>(smem_raw);
-    float* tile = reinterpret_cast<float*>(smem_raw + PM_MAX_SRC * sizeof(PmView));
+    float* tile = reinterpret_cast<float*>(smem_raw + views_bytes(F.nsrc));
     const int x0 = blockIdx.x * BW, y0 = blockIdx.y * BH;
     stage_tile<SCALE, BH>(tile, sviews, gviews, F, x0, y0);
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     if (x >= F.W || y >= F.H) return;
     DevCtx<T::PITCH, CL, SC> c;
     c.centre = tile + (threadIdx.y + T::R) * T::PITCH + (threadIdx.x + T::R);
+    c.wtab = tile + T::FLOATS + threadIdx.y * BW + threadIdx.x;
     c.views = sviews;
     c.tex = (cudaTextureObject_t)F.tex;
     c.scale = F.tex_scale;
@@ -178,13 +194,14 @@ __global__ void __launch_bounds__(BW* BH, MIN_BLOCKS) pm_ncc_bench_kernel(const 
     using T = Tile<SCALE, BH>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PmView* sviews = reinterpret_cast<PmView*>(smem_raw);
-    float* tile = reinterpret_cast<float*>(smem_raw + PM_MAX_SRC * sizeof(PmView));
+    float* tile = reinterpret_cast<float*>(smem_raw + views_bytes(F.nsrc));
     const int x0 = blockIdx.x * BW, y0 = blockIdx.y * BH;
     stage_tile<SCALE, BH>(tile, sviews, gviews, F, x0, y0);
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     if (x >= F.W || y >= F.H) return;
     DevCtx<T::PITCH, false, SC> c;
     c.centre = tile + (threadIdx.y + T::R) * T::PITCH + (threadIdx.x + T::R);
+    c.wtab = tile + T::FLOATS + threadIdx.y * BW + threadIdx.x;
     c.views = sviews;
     c.tex = (cudaTextureObject_t)F.tex;
     c.scale = F.tex_scale;
@@ -216,6 +233,7 @@ __global__ void __launch_bounds__(BW* BH) pm_geom_map_kernel(const PmFrame F, co
     if (x >= F.W || y >= F.H) return;
     DevCtx<1, false, false> c;
     c.centre = nullptr;
+    c.wtab = nullptr;
     c.views = sviews;
     c.tex = (cudaTextureObject_t)F.tex;
     const int idx = y * F.W + x;
@@ -237,6 +255,7 @@ __global__ void __launch_bounds__(256) pm_filter_kernel(const PmFrame F, pm_f4* 
     planes[y * F.W + x].w = pm_median_depth(planes, costs, F.W, F.H, x, y);
 }
 
+#if PM_EXACT
 __global__ void __launch_bounds__(256) pm_export_depth_kernel(const pm_f4* planes, float* out, int W, int H, int pitch_f) {
     const int x = blockIdx.x * BW + threadIdx.x, y = blockIdx.y * BH + threadIdx.y;
     if (x >= W || y >= H) return;
@@ -261,10 +280,11 @@ __global__ void pm_uniform_stream_kernel(unsigned long long seed, int x, int y, 
     pm_rng_init(rs, pm_mix_seed(seed, (uint32_t)x, (uint32_t)y));
     for (int i = 0; i < n; ++i) out[i] = pm_uniform(rs);
 }
+#endif  // PM_EXACT
 
 template <int SCALE, int ROWS>
-constexpr size_t smem_bytes() {
-    return PM_MAX_SRC * sizeof(PmView) + Tile<SCALE, ROWS>::FLOATS * sizeof(float);
+inline size_t smem_bytes(int nsrc) {
+    return views_bytes(nsrc) + (Tile<SCALE, ROWS>::FLOATS + WT_FLOATS) * sizeof(float);
 }
 inline size_t sweep_smem(size_t base, int nsrc) { return base + (PM_CA_SMEM ? (size_t)8 * nsrc * BW * BH * sizeof(float) : 0); }
 
@@ -297,13 +317,14 @@ inline cudaError_t allow_smem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-}  // namespace
+}  // namespace PM_ARITH_NS
 
 // ---------------------------------------------------------------------------------------------- launchers
+namespace PM_ARITH_NS {
 cudaError_t pm_launch_init(const PmFrame& F, const PmState& S, const PmView* gviews, unsigned long long seed, cudaStream_t st) {
     return dispatch(2, F, [&](auto s, auto cl, auto sc) {
         pm_init_kernel<decltype(s)::value, decltype(cl)::value, decltype(sc)::value>
-            <<<grid_full(F.W, F.H), dim3(BW, BH), smem_bytes<decltype(s)::value, BH>(), st>>>(F, S, gviews, seed);
+            <<<grid_full(F.W, F.H), dim3(BW, BH), smem_bytes<decltype(s)::value, BH>(F.nsrc), st>>>(F, S, gviews, seed);
     });
 }
 
@@ -312,7 +333,7 @@ cudaError_t pm_launch_sweep(const PmFrame& F, const PmState& S, const PmView* gv
     cudaError_t attr = cudaSuccess;
     cudaError_t rc = dispatch(scale, F, [&](auto s, auto cl, auto sc) {
         auto k = pm_sweep_kernel<decltype(s)::value, decltype(cl)::value, decltype(sc)::value>;
-        const size_t bytes = sweep_smem(smem_bytes<decltype(s)::value, 2 * BH>(), F.nsrc);
+        const size_t bytes = sweep_smem(smem_bytes<decltype(s)::value, 2 * BH>(F.nsrc), F.nsrc);
         attr = allow_smem(k, bytes);
         if (attr == cudaSuccess) k<<<grid_checker(F.W, F.H), dim3(BW, BH), bytes, st>>>(F, S, gviews, red, iter);
     });
@@ -330,7 +351,7 @@ cudaError_t pm_launch_ncc_map(const PmFrame& F, const PmView* gviews, const pm_f
                               cudaStream_t st) {
     return dispatch(scale, F, [&](auto s, auto cl, auto sc) {
         pm_ncc_map_kernel<decltype(s)::value, decltype(cl)::value, decltype(sc)::value>
-            <<<grid_full(F.W, F.H), dim3(BW, BH), smem_bytes<decltype(s)::value, BH>(), st>>>(F, gviews, planes, out);
+            <<<grid_full(F.W, F.H), dim3(BW, BH), smem_bytes<decltype(s)::value, BH>(F.nsrc), st>>>(F, gviews, planes, out);
     });
 }
 
@@ -341,8 +362,8 @@ cudaError_t pm_launch_ncc_bench(const PmFrame& F, const PmView* gviews, const pm
     const dim3 g = grid_full(F.W, F.H), b(BW, BH);
 #define PM_NB(S, T)                                                                                                    \
     if (scale == S && taps == T) {                                                                                     \
-        if (sc) pm_ncc_bench_kernel<S, T, true><<<g, b, smem_bytes<S, BH>(), st>>>(F, gviews, planes, nviews, reps, out, counter);  \
-        else pm_ncc_bench_kernel<S, T, false><<<g, b, smem_bytes<S, BH>(), st>>>(F, gviews, planes, nviews, reps, out, counter);    \
+        if (sc) pm_ncc_bench_kernel<S, T, true><<<g, b, smem_bytes<S, BH>(F.nsrc), st>>>(F, gviews, planes, nviews, reps, out, counter);  \
+        else pm_ncc_bench_kernel<S, T, false><<<g, b, smem_bytes<S, BH>(F.nsrc), st>>>(F, gviews, planes, nviews, reps, out, counter);    \
     }
     PM_NB(0, 3) PM_NB(0, 4) PM_NB(0, 5) PM_NB(0, 6) PM_NB(1, 6) PM_NB(2, 6)
 #undef PM_NB
@@ -355,6 +376,9 @@ cudaError_t pm_launch_geom_map(const PmFrame& F, const PmView* gviews, const pm_
     return cudaGetLastError();
 }
 
+}  // namespace PM_ARITH_NS
+
+#if PM_EXACT   // helper kernels without arithmetic of the path: once per library
 cudaError_t pm_launch_convert(const void* in, size_t in_pitch, int in_is_u8, void* out, int out_fmt, int W, int H, cudaStream_t st) {
     const dim3 g((W + 31) / 32, (H + 7) / 8), b(32, 8);
     const unsigned char* i = (const unsigned char*)in;
@@ -375,7 +399,6 @@ cudaError_t pm_launch_export_depth(const pm_f4* planes, float* out, int W, int H
     return cudaGetLastError();
 }
 
-#if PM_LITERAL_NCC == 2
 namespace {
 __global__ void pm_literal_table_kernel(float one, float sigma_spatial, float sigma_color, float* out20) {
     pm_literal_table(one, sigma_spatial, sigma_color, out20);
@@ -385,9 +408,9 @@ cudaError_t pm_launch_literal_table(float sigma_spatial, float sigma_color, floa
     pm_literal_table_kernel<<<1, 1, 0, st>>>(1.0f, sigma_spatial, sigma_color, out20_dev);
     return cudaGetLastError();
 }
-#endif
 
 cudaError_t pm_launch_uniform_stream(unsigned long long seed, int x, int y, int n, float* out, cudaStream_t st) {
     pm_uniform_stream_kernel<<<1, 1, 0, st>>>(seed, x, y, n, out);
     return cudaGetLastError();
 }
+#endif  // PM_EXACT

@@ -3,6 +3,9 @@
 #ifndef MPMVS_PM_VIEWS_H
 #define MPMVS_PM_VIEWS_H
 #include "../../include/mpmvs_b200.h"
+#include <float.h>
+#include <math.h>
+
 #include "pm_core.cuh"
 
 namespace pmv {
@@ -41,6 +44,37 @@ inline M3 k_homography(const float* K) {
 
 }  // namespace pmv
 
+// The hypothesis-invariant head of ComputeHomography, cu:233-247 (exact arithmetic): R_relative = R_s R_r^T and
+// t_relative = R_s (C_r - C_s) with the roundings of the reference's compiled kernels. nvcc turns its `a*b + c*d + e*f`
+// into FFMA(e, f, FFMA(a, b, FMUL(c, d))) -- the MIDDLE product is the rounded one (SASS of oracle/_ref, RefNccMap and
+// BlackPixelUpdate) -- all with .FTZ. In the library (this header compiled by nvcc's host pass) the same operations are
+// done with fmaf and flush-to-zero, so the values are the bits the reference forms on the device; in the test-only host
+// emulation (plain g++) it is the oracle's unfused left-to-right arithmetic, like everything else there.
+namespace pmv {
+inline float ftz(float x) { return (x > -FLT_MIN && x < FLT_MIN) ? (x < 0 ? -0.0f : 0.0f) : x; }
+inline float dot3_ref(float a, float b, float c, float d, float e, float f) {
+#if defined(__CUDACC__)
+    a = ftz(a); b = ftz(b); c = ftz(c); d = ftz(d); e = ftz(e); f = ftz(f);
+    const float m = ftz(c * d);
+    return ftz(fmaf(e, f, ftz(fmaf(a, b, m))));
+#else
+    return a * b + c * d + e * f;
+#endif
+}
+}  // namespace pmv
+inline void pm_view_prep(const mpmvs_camera& rc, PmView& V) {
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b)
+            V.Rrel[3 * a + b] = pmv::dot3_ref(V.sR[3 * a], rc.R[3 * b], V.sR[3 * a + 1], rc.R[3 * b + 1], V.sR[3 * a + 2], rc.R[3 * b + 2]);
+#if defined(__CUDACC__)
+    const float c0 = pmv::ftz(pmv::ftz(rc.C[0]) - pmv::ftz(V.sC[0])), c1 = pmv::ftz(pmv::ftz(rc.C[1]) - pmv::ftz(V.sC[1])),
+                c2 = pmv::ftz(pmv::ftz(rc.C[2]) - pmv::ftz(V.sC[2]));
+#else
+    const float c0 = rc.C[0] - V.sC[0], c1 = rc.C[1] - V.sC[1], c2 = rc.C[2] - V.sC[2];
+#endif
+    for (int a = 0; a < 3; ++a) V.trel[a] = pmv::dot3_ref(V.sR[3 * a], c0, V.sR[3 * a + 1], c1, V.sR[3 * a + 2], c2);
+}
+
 inline void pm_build_view_consts(const mpmvs_camera& rc, const mpmvs_camera& sc, PmView& V) {
     using namespace pmv;
     const M3 Rr = from(rc.R), Rs = from(sc.R);
@@ -74,10 +108,9 @@ inline void pm_build_view_consts(const mpmvs_camera& rc, const mpmvs_camera& sc,
     V.dh = sc.height;
     V.dpitch = sc.width;
     V.depth = nullptr;
-#if PM_LITERAL_WARP
     for (int i = 0; i < 9; ++i) { V.sK[i] = sc.K[i]; V.sR[i] = sc.R[i]; }
     for (int i = 0; i < 3; ++i) { V.st[i] = sc.t[i]; V.sC[i] = sc.C[i]; }
-#endif
+    pm_view_prep(rc, V);
 }
 
 
@@ -93,23 +126,16 @@ inline PmFrame pm_make_frame(const mpmvs_camera& c, int n, float depth_min, floa
     F.col_k = (float)(log2e / (2.0 * sigma_color * sigma_color));
     F.W = c.width; F.H = c.height; F.nsrc = n - 1; F.top_k = top_k;
     F.geom = geom ? 1 : 0; F.planar = planar ? 1 : 0;
-#if PM_LITERAL_WARP
     for (int i = 0; i < 9; ++i) F.K[i] = c.K[i];
     for (int i = 0; i < 3; ++i) { F.t[i] = c.t[i]; F.C[i] = c.C[i]; }
     F.one = 1;
     F.sigma_spatial = sigma_spatial; F.sigma_color = sigma_color;
-#if PM_LITERAL_NCC == 2
-    {   // host values (libm); the CUDA library overwrites them with the device's own (pm_capi.cu: literal_table)
+    {   // host values (libm); the CUDA library overwrites them with the device's own (pm_capi.cu: mpmvs_create)
         float t[20];
         pm_literal_table(1.0f, sigma_spatial, sigma_color, t);
         for (int k = 0; k < 18; ++k) F.lit_sd[k / 6][k % 6] = t[k];
         F.lit_rcp_spatial = t[18]; F.lit_rcp_color = t[19];
     }
-#else
-    for (int k = 0; k < 18; ++k) F.lit_sd[k / 6][k % 6] = 0.f;
-    F.lit_rcp_spatial = F.lit_rcp_color = 0.f;
-#endif
-#endif
     return F;
 }
 #endif

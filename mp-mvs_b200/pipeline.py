@@ -52,7 +52,9 @@ class PipelineConfig:
     in_flight: int = 8                # reference images a rank keeps in flight (host threads; the C ABI releases the GIL)
     max_src: int = 20                 # "Max source images num"
     seed: int = 0
-    tex_format: int = 2               # capi.TEX_U8: views are 8-bit grey levels as decoded from the JPEGs
+    arithmetic: str = "exact"         # mpmvs_set_arithmetic: "exact" = the reference's kernel results bit for bit, "fast"
+    tex_format: Optional[int] = None  # capi.TEX_*; None = float32 with the exact arithmetic (what its bit-identity needs),
+                                      # 8-bit with the fast one (views are 8-bit grey levels as decoded from the JPEGs)
     keep_normals: bool = True
 
 
@@ -102,10 +104,10 @@ class _NoTurn:
 class CudaEngine:
     """One reference image on one GPU: a resident `mpmvs_problem` (capi.PatchMatch)."""
 
-    def __init__(self, device: int, cache, ids: Sequence[int], cams_packed: np.ndarray):
+    def __init__(self, device: int, cache, ids: Sequence[int], cams_packed: np.ndarray, arithmetic: str = "exact", stream: Optional[int] = None):
         from . import capi
 
-        self.pm = capi.PatchMatch(device)
+        self.pm = capi.PatchMatch(device, stream=stream).set_arithmetic(arithmetic)
         self.pm.set_problem_cached(cache, list(ids), cams_packed)
         self.prior_stats = None
 
@@ -186,6 +188,10 @@ class DensePipeline:
             for k, ref in enumerate(shard_refs(self.ref_ids, r, world)):
                 self.slot[ref] = r * self.block + k
         self.gathered = None          # [world * block, H, W] float32: depth maps of the previous pass
+        self.gather_bufs = None       # the two buffers `gathered` alternates between (Jacobi double buffering), allocated once
+        self.gather_turn = 0
+        self.zero_map = None          # depth map of a source that is no reference image of the scene (no estimate): all 0
+        self.streams = []             # CUDA streams the engines work on (in_flight of them, shared round-robin)
         self.cache = None
 
     # ------------------------------------------------------------------------------------------ set-up
@@ -198,36 +204,63 @@ class DensePipeline:
         if self.engine_factory is None:
             from . import capi
 
-            self.cache = capi.ImageCache(self.device, self.W, self.H, max(1, len(need)), self.cfg.tex_format)
+            fmt = self.cfg.tex_format
+            if fmt is None:
+                fmt = capi.TEX_F32 if self.cfg.arithmetic == "exact" else capi.TEX_U8
+            self.cache = capi.ImageCache(self.device, self.W, self.H, max(1, len(need)), fmt)
             for i in need:
                 self.cache.put(i, self.images[i])
-        for ref in self.my_refs:
+            # the engines work on `in_flight` torch streams, so that the exchange can be ordered against them with stream
+            # events instead of device-wide synchronisation
+            self.streams = [self.torch.cuda.Stream(device=self.tdev) for _ in range(max(1, self.cfg.in_flight))]
+        for k, ref in enumerate(self.my_refs):
             ids = self.problem_ids(ref)
             packed = self.io.pack_cameras([self.cams[i] for i in ids])
             if self.engine_factory is None:
-                self.engines[ref] = CudaEngine(self.device, self.cache, ids, packed)
+                self.engines[ref] = CudaEngine(self.device, self.cache, ids, packed, self.cfg.arithmetic,
+                                               self.streams[k % len(self.streams)].cuda_stream)
             else:
                 self.engines[ref] = self.engine_factory(ids, [self.images[i] for i in ids], packed)
+        if self.cfg.geom_iterations > 0:
+            # both gather buffers once, zero-filled (slots past the last image of a short block, and `zero_map`, stay 0):
+            # no allocation and no zero-fill inside a pass
+            n = self.world * self.block
+            self.gather_bufs = [self.torch.zeros((n, self.H, self.W), dtype=self.torch.float32, device=self.tdev)
+                                for _ in range(2 if self.cfg.geom_iterations > 1 else 1)]
+            self.zero_map = self.torch.zeros((self.H, self.W), dtype=self.torch.float32, device=self.tdev)
+            self._sync_torch()
         return len(need)
 
     # ------------------------------------------------------------------------------------------ exchange
     def _exchange(self, st: PassStats):
-        """All-gather of this pass's depth maps: rank r fills block r of a fresh [world*block, H, W] buffer."""
+        """All-gather of this pass's depth maps: every engine writes its map straight into this rank's block of the gather
+        buffer (mpmvs_export_depth_device), NCCL gathers the blocks in place. The buffers are allocated once (setup) and
+        alternate (Jacobi double buffering); ordering against the engines' streams is by stream events, not by device-wide
+        synchronisation."""
         torch = self.torch
+        out = self.gather_bufs[self.gather_turn % len(self.gather_bufs)]
+        self.gather_turn += 1
+        mine = out[self.rank * self.block:(self.rank + 1) * self.block]
+        cuda = self.tdev.type == "cuda"
+        cur = torch.cuda.current_stream(self.tdev) if cuda else None
+        if cuda and self.streams:
+            for s_ in self.streams:          # the previous pass may still be reading this buffer's other twin only; but its
+                s_.wait_stream(cur)          # exports must not overtake an all-gather still in flight on `cur`
         t0 = self._tick()
-        mine = torch.zeros((self.block, self.H, self.W), dtype=torch.float32, device=self.tdev)
-        self._sync_torch()             # the engines write on their own streams: the zero-fill must have landed
         for k, ref in enumerate(self.my_refs):
             self.engines[ref].export_depth(mine[k])
-        for ref in self.my_refs:
-            self.engines[ref].synchronize()
-        if self.world > 1:
-            out = torch.empty((self.world * self.block, self.H, self.W), dtype=torch.float32, device=self.tdev)
-            self.dist.all_gather_into_tensor(out, mine)
-            self._sync_torch()         # ... and the gathered maps must be complete before the engines' streams read them
+        if cuda and self.streams:
+            for s_ in self.streams:
+                cur.wait_stream(s_)          # the gather starts when every engine stream has written its maps
         else:
-            out = mine
-        self.gathered = out            # the previous buffer is dropped only now: Jacobi double buffering
+            for ref in self.my_refs:
+                self.engines[ref].synchronize()
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(out, mine)       # in place: `mine` is this rank's block of `out`
+        if cuda and self.streams:
+            for s_ in self.streams:
+                s_.wait_stream(cur)          # ... and the next pass's kernels start when the gathered maps are complete
+        self.gathered = out
         st.exchange_ms = self._tock(t0)
 
     def _sync_torch(self):
@@ -267,7 +300,9 @@ class DensePipeline:
         def one(ref):
             seed = stage_seed(self.cfg.seed, ref, stage)
             if geom:
-                views = [prev[self.slot[i]] for i in self.problem_ids(ref)[1:]]
+                # a source without an estimate of its own (not a reference image of the scene) has depth 0 everywhere, which
+                # ComputeGeomConsistencyCost answers with the maximum cost (cu:627-629) -- what the C++ hosts do as well
+                views = [prev[self.slot[i]] if i in self.slot else self.zero_map for i in self.problem_ids(ref)[1:]]
                 self.engines[ref].process(seed, True, planar, [v.data_ptr() for v in views] if self.tdev.type == "cuda" else views, **extra)
             else:
                 self.engines[ref].process(seed, False, planar, **extra)

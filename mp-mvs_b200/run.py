@@ -43,6 +43,55 @@ def load_image(folder: str, image_id: int, max_size: int):
     return out, nw / np.float32(w), nh / np.float32(h)
 
 
+def image_size(folder: str, image_id: int):
+    """(width, height) of an image of the dense folder without decoding it: the PGM header of the sidecar, else the JPEG's
+    SOF segment. Falls back to decoding."""
+    pgm = os.path.join(folder, f"{image_id:08d}.pgm")
+    if os.path.exists(pgm):
+        with open(pgm, "rb") as f:
+            tok = f.read(64).split()
+        if tok and tok[0] == b"P5":
+            return int(tok[1]), int(tok[2])
+    jpg = os.path.join(folder, f"{image_id:08d}.jpg")
+    try:
+        with open(jpg, "rb") as f:
+            if f.read(2) == b"\xff\xd8":
+                while True:
+                    b = f.read(1)
+                    while b and b != b"\xff":
+                        b = f.read(1)
+                    m = f.read(1)
+                    while m == b"\xff":
+                        m = f.read(1)
+                    if not m:
+                        break
+                    k = m[0]
+                    if k in (0xD8, 0x01) or 0xD0 <= k <= 0xD7:
+                        continue
+                    n = int.from_bytes(f.read(2), "big")
+                    if 0xC0 <= k <= 0xCF and k not in (0xC4, 0xC8, 0xCC):      # SOFn: precision, height, width
+                        seg = f.read(5)
+                        return int.from_bytes(seg[3:5], "big"), int.from_bytes(seg[1:3], "big")
+                    f.seek(n - 2, 1)
+    except OSError:
+        pass
+    import cv2
+
+    img = cv2.imread(pgm if os.path.exists(pgm) else jpg, cv2.IMREAD_GRAYSCALE)
+    if img is None:
+        raise FileNotFoundError(f"Can not read this image ! {image_id:08d}")
+    return img.shape[1], img.shape[0]
+
+
+def resized_size(w: int, h: int, max_size: int):
+    """PatchMatchInit's resize rule (PatchMatch.cpp:893-925): (new width, new height, scale x, scale y)."""
+    if w <= max_size and h <= max_size:
+        return w, h, 1.0, 1.0
+    factor = min(np.float32(max_size) / np.float32(w), np.float32(max_size) / np.float32(h))
+    nw, nh = int(round(float(np.float32(w) * factor))), int(round(float(np.float32(h) * factor)))
+    return nw, nh, nw / np.float32(w), nh / np.float32(h)
+
+
 def sky_image_size(w: int, h: int, max_size: int):
     """Size rule of GenerateSkyRegionMask (PatchMatch.cpp:21-33): the image size PatchMatch worked at."""
     if w <= max_size and h <= max_size:
@@ -110,20 +159,21 @@ def load_scene(cfg: dict, rank: int, world: int):
 
     with ThreadPoolExecutor(min(16, os.cpu_count() or 1)) as ex:
         decoded = dict(zip(need, ex.map(lambda i: load_image(os.path.join(inp, "images"), i, int(cfg["Max image size"])), need)))
+    max_size = int(cfg["Max image size"])
     for i in sorted(set(refs) | set(need)):
         cam = io_formats.read_cam(os.path.join(inp, "cams", f"{i:08d}_cam.txt"))
         if i in need:
             img, sx, sy = decoded[i]
             images[i] = img
-            cam.K = cam.K.copy()
-            cam.K[0, 0] *= sx; cam.K[0, 2] *= sx; cam.K[1, 1] *= sy; cam.K[1, 2] *= sy
-            cam.height, cam.width = img.shape
+            h, w = img.shape
+        else:
+            # an image another rank estimates: this rank (rank 0: fusion) still needs its camera AT THE SIZE PatchMatch worked
+            # at -- the same K scaling as RescaleImageAndCamera (PatchMatch.cpp:906-921), from the header of the file
+            w, h, sx, sy = resized_size(*image_size(os.path.join(inp, "images"), i), max_size)
+        cam.K = cam.K.copy()
+        cam.K[0, 0] *= sx; cam.K[0, 2] *= sx; cam.K[1, 1] *= sy; cam.K[1, 2] *= sy
+        cam.height, cam.width = h, w
         cams[i] = cam
-    # cameras of images this rank does not load still need a size for the gather buffer: all views share one size
-    h0, w0 = images[need[0]].shape
-    for c in cams.values():
-        if not c.width:
-            c.height, c.width = h0, w0
     return entries, cams, images
 
 
@@ -133,12 +183,10 @@ def main():
     ap.add_argument("--seed", type=int, default=0x2333)
     ap.add_argument("--in-flight", type=int, default=8, help="reference images in flight per GPU (host threads: the planar-prior triangulation is host work)")
     ap.add_argument("--fusion", type=int, default=1, help="fuse the depth maps on rank 0's GPU and write MPMVS_model.ply")
-    ap.add_argument("--fidelity", default="fast", choices=["fast", "exact"],
-                    help="exact: the fidelity build of the kernels (variants/libmpmvs_b200_literal2.so, float32 view storage): the "
-                         "reference's kernel results bit for bit, about 25 %% slower than the shipped kernels")
+    ap.add_argument("--arithmetic", "--fidelity", dest="arithmetic", default="exact", choices=["exact", "fast"],
+                    help="exact (default): the reference's kernel results bit for bit, float32 view storage; fast: the library's "
+                         "hoisted arithmetic with 8-bit view storage, statistically equal results (mpmvs_set_arithmetic)")
     args = ap.parse_args()
-    if args.fidelity == "exact":          # the library is chosen when mpmvs_b200.capi is first imported (below)
-        os.environ["MPMVS_LIB_VARIANT"] = "literal2"
     import torch
 
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -157,7 +205,8 @@ def main():
     pcfg = pipeline.PipelineConfig(geom_iterations=int(cfg["Geometric consistency iterations"]), max_src=int(cfg["Max source images num"]),
                                    seed=args.seed, planar_prior=bool(int(cfg["Planer prior"])),
                                    geom_planar_prior=bool(int(cfg["Geometric consistency planer prior"])),
-                                   tex_format=capi.TEX_F32 if (resized or args.fidelity == "exact") else capi.TEX_U8, in_flight=args.in_flight)
+                                   tex_format=capi.TEX_F32 if (resized or args.arithmetic == "exact") else capi.TEX_U8, in_flight=args.in_flight,
+                                   arithmetic=args.arithmetic)
     p = pipeline.DensePipeline(entries, cams, images, pcfg, rank=rank, world=world, device=local, dist=dist)
     p.setup()
     t1 = time.time()
@@ -182,6 +231,7 @@ def main():
         dist.barrier()
     t4 = t3
     n_points = None
+    p.destroy()            # the resident PatchMatch state (76 B/px per reference image) is not needed any more: free it before fusion
     if rank == 0 and args.fusion:
         # RunFusion (PatchMatch.cpp:287-504) on the GPU: every rank has written its maps, rank 0 reads them back
         est = sorted(e.ref_id for e in entries if e.estimate)
@@ -211,7 +261,6 @@ def main():
         print(f"cost time is {(t2 - t1) * 1e6:.10f} us")
         if n_points is not None:
             print(f"fusion: {n_points} points in {t4 - t3:.2f} s (load + GPU fusion + ply)")
-    p.destroy()
     if dist is not None:
         dist.destroy_process_group()
 

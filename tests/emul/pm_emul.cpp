@@ -45,6 +45,8 @@ float tex2d(const float* img, int w, int h, float x, float y) {
 struct HostCtx {
     const Emu* E;
     int x, y;
+    mutable float wtab[36];   // the thread's bilateral-weight table (shared memory in the kernels)
+    float& wt(int k) const { return wtab[k]; }
     float ref(int dx, int dy) const {
         return E->images[0][(size_t)clampi(y + dy, 0, E->H - 1) * E->W + clampi(x + dx, 0, E->W - 1)];
     }

@@ -75,8 +75,8 @@ def test_roofline_constants():
     assert bench.ncu_traffic("dtu") is None
 
 
-def test_exact_arm_never_takes_the_headline_down():
-    """`fidelity_exact` is measured by a child process; whatever happens to it (here: no GPU) must come back as an `error`
+def test_fast_arm_never_takes_the_headline_down():
+    """`arithmetic_fast` is measured after the headline; whatever happens to it (here: no GPU) must come back as an `error`
     entry, not as an exception in the process that prints the headline line."""
     import types
 
@@ -87,5 +87,7 @@ def test_exact_arm_never_takes_the_headline_down():
     sys.path.insert(0, ROOT)
     import bench
 
-    res = bench.exact_arm(types.SimpleNamespace(steps=1, warmup=1, workload="plane", in_flight=2))
+    prob = {"width": 8, "height": 8, "images": [None] * 3}
+    res = bench.fast_arm(types.SimpleNamespace(steps=1, warmup=1, workload="plane", in_flight=2, arithmetic="exact", tex="f32"), 0, 1, 0, prob,
+                         lambda: None, lambda x: x)
     assert set(res) == {"error"} and res["error"]

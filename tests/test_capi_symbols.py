@@ -41,7 +41,9 @@ def test_camera_struct_is_binary_compatible():
 def test_error_strings_and_version():
     L = capi.lib()
     assert L.mpmvs_version() >= 100
-    assert capi.build_flavor() == "shipped"      # the in-tree library; variants/libmpmvs_b200_literal2.so answers "literal2"
+    assert capi.build_flavor() == "exact+fast"   # ONE library with both arithmetics; a handle picks at run time
+    assert L.mpmvs_arithmetic_name(0) == b"exact" and L.mpmvs_arithmetic_name(1) == b"fast"
+    assert capi.default_arithmetic() == os.environ.get("MPMVS_ARITHMETIC", "exact")
     assert b"no CUDA device" in L.mpmvs_error_string(-2)
     assert L.mpmvs_error_string(0) == b"ok"
 

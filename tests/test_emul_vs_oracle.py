@@ -171,18 +171,18 @@ def test_restructurings_are_bit_identical(libs):
                 np.testing.assert_array_equal(x, y)
 
 
-@pytest.mark.parametrize("level", [1, 2])
 @pytest.mark.parametrize("name", CASES)
-def test_literal_variant_is_bit_identical_to_the_oracle(libs, name, level):
-    """-DPM_LITERAL_NCC=1 (pm_core.cuh): homography, tap coordinates, bilateral weights, NCC sums and the geometric cost in
-    the reference's own operation order. Instantiated on the host, the product's per-pixel templates must then reproduce
-    the literal restatement (oracle/pm_oracle.c) BIT FOR BIT over whole runs in all three modes -- every plane, cost,
-    geometric cost and RNG draw. This pins the control flow and every piece of arithmetic outside the NCC of the shipped
-    build too (the two builds differ only inside `#if PM_LITERAL_*`)."""
+def test_exact_arithmetic_is_bit_identical_to_the_oracle(libs, name):
+    """-DPM_EXACT=1 (pm_core.cuh, namespace pm_exact: one of the two arithmetics compiled into the library): homography, tap
+    coordinates, bilateral weights, NCC sums and the geometric cost in the reference's own operation order, every rounding
+    written down. Instantiated on the host (unfused arithmetic, as the plain-C oracle), the product's per-pixel templates must
+    reproduce the literal restatement (oracle/pm_oracle.c) BIT FOR BIT over whole runs in all three modes -- every plane, cost,
+    geometric cost and RNG draw. This pins the control flow and every piece of arithmetic outside the NCC of the fast
+    arithmetic too (the two differ only inside `#if PM_EXACT`). What the GPU adds -- which products nvcc fuses -- is checked
+    on the SASS (test_sass_equivalence.py) and on the B200 (test_zz_fidelity_build_gpu.py)."""
     from conftest import build_emul as be
 
-    # level 1: run-time tap loops, the compiler fuses; level 2: unrolled taps, every rounding pinned (host: unfused, as the oracle)
-    libs.LIBS["emul_literal"] = (be("_literal" if level == 1 else "_literal2", [f"-DPM_LITERAL_NCC={level}"]), "emu_")
+    libs.LIBS["emul_literal"] = (be("_exact", ["-DPM_EXACT=1"]), "emu_")
     c = make_case(name)
     o = libs.Oracle("cpu").set_problem(c["images"], c["cams"])
     e = libs.Oracle("emul_literal").set_problem(c["images"], c["cams"])

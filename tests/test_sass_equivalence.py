@@ -1,5 +1,5 @@
-"""The fidelity build (-DPM_LITERAL_NCC=2, mp-mvs_b200/variants/libmpmvs_b200_literal2.so) must keep COMPILING to the
-reference's arithmetic: under --use_fast_math its bit-identity with the reference on the GPU
+"""The exact arithmetic of the library (pm_kernels.cu compiled with -DPM_EXACT=1: the pm_exact:: kernels of
+mp-mvs_b200/libmpmvs_b200.so) must keep COMPILING to the reference's arithmetic: under --use_fast_math its bit-identity with the reference on the GPU
 (tests/test_zz_fidelity_build_gpu.py) depends on which products end up fused into FMAs, and that is only visible in the
 SASS. This CPU test disassembles both builds (cuobjdump, no GPU) and compares the floating-point expression trees with
 tests/tools/sass_expr.py, so an edit of pm_core.cuh that changes a rounding is caught where there is no GPU."""
@@ -15,14 +15,16 @@ from conftest import ROOT
 sys.path.insert(0, os.path.join(ROOT, "tests", "tools"))
 
 REF = os.path.join(ROOT, "oracle", "_ref", "libmpmvs_ref.so")
-LIT = os.path.join(ROOT, "mp-mvs_b200", "variants", "libmpmvs_b200_literal2.so")
+LIT = os.path.join(ROOT, "mp-mvs_b200", "libmpmvs_b200.so")
+SWEEP = "pm_exact15pm_sweep_kernelILi%dELb0ELb0"      # pm_exact::pm_sweep_kernel<scale, false, false>
+NCC_MAP = "pm_exact17pm_ncc_map_kernelILi0ELb0ELb0"
 CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
 
 
 @pytest.fixture(scope="module")
 def sass(tmp_path_factory):
     if not (os.path.exists(REF) and os.path.exists(LIT) and os.path.exists(CUOBJDUMP)):
-        pytest.skip("needs oracle/_ref/libmpmvs_ref.so, the literal2 variant library (build()) and cuobjdump")
+        pytest.skip("needs oracle/_ref/libmpmvs_ref.so, the library (build()) and cuobjdump")
     d = tmp_path_factory.mktemp("sass")
     out = {}
     for tag, lib in (("ref", REF), ("lit", LIT)):
@@ -39,20 +41,21 @@ def test_source_coordinates_are_the_reference_expression(sass, scale):
     that is still in registers at that point is taken as the leaf it is in the reference's first two inlined copies)."""
     import sass_expr
 
-    ours = sass_expr.source_coordinate_trees(sass["lit"], f"pm_sweep_kernelILi{scale}ELb0ELb0")
+    ours = sass_expr.source_coordinate_trees(sass["lit"], SWEEP % scale)
     assert len(ours) == 36
-    refs = sass_expr.source_coordinate_trees(sass["ref"], "BlackPixelUpdate")
+    # the relative pose R_s R_r^T, R_s (C_r - C_s) is hoisted in the product (formed once per problem with the same
+    # operations, pm_views.h: pm_view_prep) and arrives as loaded values: those subtrees of the reference count as leaves
+    refs = sass_expr.source_coordinate_trees(sass["ref"], "BlackPixelUpdate", fold=True)
     assert len(refs) >= 3                                    # cost vector, current plane, refinement: three inlined copies
-    assert set(refs) == set(sass_expr.source_coordinate_trees(sass["ref"], "RedPixelUpdate"))
-    assert set(ours) <= set(refs), "a source coordinate of the fidelity build is not one of the reference's expressions"
-    assert sass_expr.compare(sass["ref"], "BlackPixelUpdate", sass["lit"], f"pm_sweep_kernelILi{scale}ELb0ELb0")
+    assert set(refs) == set(sass_expr.source_coordinate_trees(sass["ref"], "RedPixelUpdate", fold=True))
+    assert sass_expr.compare(sass["ref"], "BlackPixelUpdate", sass["lit"], SWEEP % scale)
 
 
 def test_ncc_test_hook_matches_too(sass):
     import sass_expr
 
-    ref = sass_expr.source_coordinate_trees(sass["ref"], "RefNccMap")
-    ours = sass_expr.source_coordinate_trees(sass["lit"], "pm_ncc_map_kernelILi0ELb0ELb0")
+    ref = sass_expr.source_coordinate_trees(sass["ref"], "RefNccMap", fold=True)
+    ours = sass_expr.source_coordinate_trees(sass["lit"], NCC_MAP)
     assert len(ours) == 36 and len(set(ref)) == 1 and set(ours) == set(ref)
 
 
@@ -61,20 +64,20 @@ def test_no_rsqrt_in_the_ncc_tail(sass):
     not one MUFU.RSQ: the test hook kernel contains the NCC and nothing else that takes a square root."""
     import sass_expr
 
-    body = [ins for _, ins in sass_expr.function_body(sass["lit"], "pm_ncc_map_kernelILi0ELb0ELb0")]
+    body = [ins for _, ins in sass_expr.function_body(sass["lit"], NCC_MAP)]
     assert not any("MUFU.RSQ" in i for i in body)
     assert any("MUFU.SQRT" in i for i in body) and any("MUFU.RCP" in i for i in body)
     ref = [ins for _, ins in sass_expr.function_body(sass["ref"], "RefNccMap")]
     assert not any("MUFU.RSQ" in i for i in ref)
 
 
-# md5 of the instruction text of the fidelity build's pipeline kernels (sass_expr.pipeline_checksum) as they were when
+# md5 of the instruction text of the exact arithmetic's pipeline kernels (pm_exact::*) (sass_expr.pipeline_checksum) as they were when
 # tests/test_zz_fidelity_build_gpu.py measured them bit-identical to the reference on a B200 (nvcc 12.9.86, sm_100a).
 VERIFIED_ON_GPU = "38deed19ed9b343b41d98f8be66a9bca"
 
 
 def test_fidelity_kernels_are_the_ones_verified_on_the_gpu(sass):
-    """Any edit that changes an instruction of the fidelity build's sweep / init / finalize kernels lands here first: run
+    """Any edit that changes an instruction of the exact arithmetic's sweep / init / finalize kernels lands here first: run
     tests/test_zz_fidelity_build_gpu.py on a B200 again and, if it is still bit-identical, record the new checksum
     (`python tests/tools/sass_expr.py md5 <cuobjdump -sass of the library>`). Comments and host code do not change it."""
     import sass_expr

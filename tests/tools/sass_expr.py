@@ -154,8 +154,31 @@ def main():
         print(f"  EX2 argument at {[hex(p) for p in pcs][:4]}: {c}")
 
 
-def source_coordinate_trees(path, name):
-    """Canonical trees of the x coordinate of every source-sample fetch (fma(numerator, rcp(Z), 0.5)) of a kernel."""
+# The hypothesis-invariant head of ComputeHomography (cu:233-247) as the reference's SASS forms it: R_relative[k] and
+# t_relative[k]. The product computes them once per problem (pm_views.h: pm_view_prep, same operations) and LOADS them, so
+# in a comparison these subtrees of the reference are taken as the leaves they are in ours.
+POSE_SUBTREES = ("fma(+x,x;fma(+x,x;mul(x,x)))", "fma(+add(neg(x),x),x;fma(+add(neg(x),x),x;mul(add(neg(x),x),x)))")
+
+
+def fold_pose(e, memo=None):
+    """The tree with every POSE_SUBTREES node replaced by a leaf."""
+    memo = {} if memo is None else memo
+    k = id(e)
+    if k in memo:
+        return memo[k]
+    if e[0] in ("leaf", "const"):
+        r = e
+    elif e[0] in ("FFMA",) and canon(e) in POSE_SUBTREES:
+        r = ("leaf", "pose")
+    else:
+        r = (e[0],) + tuple(fold_pose(a, memo) if isinstance(a, tuple) else a for a in e[1:])
+    memo[k] = r
+    return r
+
+
+def source_coordinate_trees(path, name, fold=False):
+    """Canonical trees of the x coordinate of every source-sample fetch (fma(numerator, rcp(Z), 0.5)) of a kernel.
+    fold: take the relative pose (POSE_SUBTREES) as leaves."""
     body = function_body(path, name)
     out = []
     for t, (_, ins) in enumerate(body):
@@ -164,9 +187,10 @@ def source_coordinate_trees(path, name):
         env = run(body[:t])
         args = [a.strip() for a in ins.split(None, 1)[1].split(",")]
         base = int(args[2].lstrip("R")) + (1 if "ARRAY" in ins else 0)
-        c = canon(env.get(f"R{base}", ("leaf", "?")))
+        e = env.get(f"R{base}", ("leaf", "?"))
+        c = canon(e)
         if c.startswith("fma(") and c.endswith(";0.5)") and "rcp(" in c:
-            out.append(c)
+            out.append(canon(fold_pose(e)) if fold else c)
     return out
 
 
@@ -186,7 +210,7 @@ def subtrees(s):
 def compare(ref_path, ref_name, our_path, our_name):
     """Are the source coordinates the same expression in both kernels? Equal trees, or equal once ONE subtree of ours is
     taken as a leaf (a hypothesis that is still in registers in our kernel where the reference reloads it from memory)."""
-    ref = source_coordinate_trees(ref_path, ref_name)[0]
+    ref = source_coordinate_trees(ref_path, ref_name, fold=True)[0]
     ours = source_coordinate_trees(our_path, our_name)
     print(f"reference {ref_name}: {ref.count('(')} nodes; ours {our_name}: {len(ours)} source fetches")
     verdicts = {}
@@ -206,7 +230,7 @@ def compare(ref_path, ref_name, our_path, our_name):
     return all(not v.startswith("DIFFERENT") for v in verdicts)
 
 
-PIPELINE_KERNELS = ("pm_sweep_kernel", "pm_init_kernel", "pm_ncc_map_kernel", "pm_geom_map", "pm_depth_normal", "pm_filter")
+PIPELINE_KERNELS = tuple("pm_exact" + k for k in ("15pm_sweep_kernel", "14pm_init_kernel", "17pm_ncc_map_kernel", "18pm_geom_map", "22pm_depth_normal", "16pm_filter"))
 
 
 def pipeline_checksum(path):

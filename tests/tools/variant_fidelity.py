@@ -3,7 +3,7 @@
 The library is chosen at import time (MPMVS_LIB_VARIANT=<name> -> mp-mvs_b200/variants/libmpmvs_b200_<name>.so, unset = the
 shipped in-tree library), so every build gets its own process:
 
-    MPMVS_LIB_VARIANT=literal2 python tests/tools/variant_fidelity.py
+    MPMVS_ARITHMETIC=exact python tests/tools/variant_fidelity.py
     python tests/tools/variant_fidelity.py                    # the shipped kernels, for comparison
     ... --modes                                                # also whole planar-prior and geometric-consistency runs
 
@@ -29,7 +29,7 @@ from parity_checks import colour_mask  # noqa: E402
 
 
 def main():
-    out = {"variant": os.environ.get("MPMVS_LIB_VARIANT", "shipped"), "library": capi.LIB_PATH, "arithmetic": capi.build_flavor(), "cases": {}}
+    out = {"variant": os.environ.get("MPMVS_LIB_VARIANT", "shipped"), "library": capi.LIB_PATH, "arithmetic": capi.default_arithmetic(), "cases": {}}
     for name in CASES:
         c = make_case(name)
         pm = capi.PatchMatch(0).set_problem(c["images"], c["cams"])
