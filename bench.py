@@ -34,9 +34,13 @@ metric = W*H*steps / seconds, summed over ranks.
            oracle/ (OpenCV Subdiv2D + plain C, one core). The reference has no CPU implementation of the kernels.
            Rank 0 only (the reference is single-GPU, src/PatchMatch.cpp:509).
 
-Multi-GPU: reference images are independent within a stage; each rank runs its own reference images,
-no data-path collective inside stage 1 -> "scaling": "weak". The depth-map exchange between stages is exercised by
-mp-mvs_b200/pipeline.py (tools/gpu_pipeline_check.py, tests/test_pipeline_gloo.py).
+Multi-GPU: two things in one line.
+  value / e2e   : the metric's configuration (configs[2]) has no geometric-consistency pass, so its reference images are
+           independent: each rank runs its own reference images, no data-path collective -> "scaling": "weak".
+  sharded_scene : the north star's multi-GPU configuration (configs[3]: 300 views 1920x1080 sharded by reference image,
+           photometric + 2 geometric-consistency passes, the depth all-gather over NVLink INSIDE the timed region) through
+           mp-mvs_b200/pipeline.py at every N, strong scaling -- `value` there is the whole scene's Mpix/s; see
+           run_sharded_scene. --scene-views 0 skips it.
 """
 from __future__ import annotations
 
@@ -440,6 +444,89 @@ def run_ours(args, rank, world, local_rank, prob, barrier, allmax, arithmetic=No
     return out
 
 
+def run_sharded_scene(args, rank, world, local_rank, dist, barrier):
+    """BASELINE.json configs[3], the north star's multi-GPU configuration, through the product's own pipeline
+    (mp-mvs_b200/pipeline.py: DensePipeline) with the exchange INSIDE the timed region: a Tanks-and-Temples-shaped ring of
+    `--scene-views` (300) views 1920x1080, 10 sources each, photometric pass + 2 geometric-consistency passes
+    (main(), /root/reference/src/main.cpp:20-41), reference images sharded over the ranks in contiguous blocks, depth maps
+    all-gathered over NVLink with NCCL between the passes instead of the reference's depths.dmb files
+    (PatchMatch.cpp:620-633 writes, :934-950 reads). STRONG scaling: the scene is fixed, so `value` at N GPUs over `value` at
+    one GPU is the speed-up. Timing: a barrier + device synchronisation on both sides, CUDA events per pass and per exchange,
+    maximum over the ranks."""
+    import torch
+
+    from mpmvs_b200 import pipeline
+
+    W, H, V = 1920, 1080, args.scene_views
+    cache = f"/dev/shm/mpmvs_scene_tnt_{V}_{W}x{H}_{os.getuid()}.npz"
+    if rank == 0 and not os.path.exists(cache):
+        t = time.time()
+        sc = synth.make_tnt_scene(width=W, height=H, n_views=V, n_src=10, workers=min(32, os.cpu_count() or 1))
+        np.savez(cache + ".tmp.npz", images=np.stack(sc.images), cams=io_formats.pack_cameras(sc.cams),
+                 pairs=np.array([[j for j, _ in sc.pairs[i]] for i in range(sc.num_views)]), gt=np.stack(sc.gt_depth).astype(np.float16))
+        os.replace(cache + ".tmp.npz", cache)
+        log(f"[bench] rendered the {V}-view ring {W}x{H} in {time.time() - t:.1f} s on {os.cpu_count()} cores")
+    barrier()
+    z = np.load(cache)
+    cams_packed = z["cams"]
+    cams = {}
+    for i in range(len(cams_packed)):
+        r = cams_packed[i]
+        cams[i] = io_formats.Camera(K=r["K"].reshape(3, 3), R=r["R"].reshape(3, 3), t=r["t"], height=int(r["height"]), width=int(r["width"]),
+                                    depth_min=float(r["depth_min"]), depth_max=float(r["depth_max"]))
+    entries = [io_formats.SceneEntry(ref_id=i, src_ids=[i] + [int(j) for j in z["pairs"][i]], estimate=True) for i in range(len(cams_packed))]
+    mine = pipeline.shard_refs(list(range(V)), rank, world)
+    need = sorted({j for i in mine for j in entries[i].src_ids})
+    all_imgs = z["images"]
+    images = {i: all_imgs[i] for i in need}           # a rank loads only its shard's reference and source views
+    cfg = pipeline.PipelineConfig(geom_iterations=2, max_src=10, seed=9, planar_prior=False, geom_planar_prior=False, in_flight=8,
+                                  arithmetic=args.arithmetic)
+    p = pipeline.DensePipeline(entries, cams, images, cfg, rank=rank, world=world, device=local_rank, dist=dist)
+    t = time.time()
+    n_cached = p.setup()
+    torch.cuda.synchronize()
+    setup_s = time.time() - t
+    if dist is not None:     # NCCL communicator and its buffers: outside the timed region
+        w = torch.zeros(1024, device="cuda")
+        o = torch.zeros(1024 * world, device="cuda")
+        dist.all_gather_into_tensor(o, w)
+    torch.cuda.synchronize()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t = time.time()
+    stats = p.run()
+    torch.cuda.synchronize()
+    barrier()
+    dt = time.time() - t
+    clocks = sampler.stop()
+    gt = z["gt"]
+    acc, comp = [], []
+    for r_ in mine[:3]:
+        planes, costs = p.engines[r_].result()
+        a_, c_ = synth.accuracy_completeness_at(planes[..., 3], costs, gt[r_].astype(np.float32))
+        acc.append(a_); comp.append(c_)
+    tt = torch.tensor([dt] + [s_.device_ms for s_ in stats] + [s_.exchange_ms for s_ in stats], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    tt = tt.tolist()
+    n = len(stats)
+    p.destroy()
+    torch.cuda.empty_cache()
+    limiting = max(range(n), key=lambda k: tt[1 + k])
+    return {"workload": f"tnt-shaped ring, {V} views {W}x{H}, 10 src views, photometric + 2 geometric-consistency passes (BASELINE.json configs[3])",
+            "scaling": "strong", "n_gpus": world, "refs": V, "refs_per_rank_max": p.block, "arithmetic": args.arithmetic,
+            "view_storage": "f32" if args.arithmetic == "exact" else "u8", "value": round(V * W * H / 1e6 / tt[0], 3), "unit": "Mpix/s",
+            "total_s": round(tt[0], 3), "schedule": [s_.name for s_ in stats], "pass_ms_max_over_ranks": [round(v, 1) for v in tt[1:1 + n]],
+            "exchange_ms_max_over_ranks": [round(v, 2) for v in tt[1 + n:]], "exchange_bytes_per_pass": V * W * H * 4,
+            "collective": "NCCL all_gather_into_tensor of the depth maps (in place, buffers preallocated) after the photometric pass and after geometric pass 0"
+                          if world > 1 else "none (one GPU: the maps are exported into the same buffer the next pass reads)",
+            "limiting_pass": stats[limiting].name, "ideal_speedup": round(V / p.block, 2), "views_cached_this_rank": n_cached,
+            "setup_s_rank0": round(setup_s, 2), "clocks": clocks,
+            "accuracy_2_5_10cm_first_refs_rank0": [[round(x, 2) for x in a_] for a_ in acc],
+            "completeness_2_5_10cm_first_refs_rank0": [[round(x, 2) for x in c_] for c_ in comp]}
+
+
 def cpu_baseline(prob, budget_s=20.0):
     """The plain-C oracle port on a centre crop of the same views (principal point shifted), all host cores."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -566,6 +653,7 @@ def main():
     ap.add_argument("--tex", default=None, choices=["f32", "f16", "u8"],
                     help="storage format of the views in HBM (default: f32 with the exact arithmetic -- the reference's, and what its "
                          "bit-identity needs -- and u8 with the fast one)")
+    ap.add_argument("--scene-views", type=int, default=300, help="views of the sharded config-4 scene (sharded_scene); 0 skips it")
     ap.add_argument("--no-fast-arm", "--no-exact-arm", dest="no_fast_arm", action="store_true",
                     help="at N=1, skip the extra measurement of the fast arithmetic (arithmetic_fast)")
     args = ap.parse_args()
@@ -606,7 +694,15 @@ def main():
         print(json.dumps(out), flush=True)
         return 0
     out = run_ours(args, rank, world, local_rank, prob, barrier, allmax)
+    scene = None
+    if args.scene_views > 0:
+        try:
+            scene = run_sharded_scene(args, rank, world, local_rank, dist, barrier)
+        except Exception as e:          # noqa: BLE001 -- every rank reaches the barrier below; the headline line survives
+            scene = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
     if rank == 0:
+        if scene is not None:
+            out["sharded_scene"] = scene
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(prob)
         if world == 1 and args.arithmetic == "exact" and not args.no_fast_arm:

@@ -103,6 +103,7 @@ def lib() -> C.CDLL:
         "mpmvs_fusion_run": [vp, vp, i, i, C.POINTER(u64), fp],
         "mpmvs_fusion_get_points": [vp, vp, u64],
         "mpmvs_fusion_set_sky_mask": [vp, i, vp],
+        "mpmvs_fusion_set_color": [vp, i, vp],
         "mpmvs_sky_mask_refine": [i, vp, vp, i, i, vp, i, i, vp, vp, fp],
         "mpmvs_build_prior": [vp, vp],
         "mpmvs_pick_vertices": [vp, i, vp, i, C.POINTER(i)],
@@ -193,6 +194,12 @@ class Fusion:
         cam = np.ascontiguousarray(cam_packed)
         assert nrm.shape == d.shape + (3,) and g.shape == d.shape
         _ck(lib().mpmvs_fusion_set_view(self.h, index, cam.ctypes.data, d.ctypes.data, nrm.ctypes.data, g.ctypes.data), "fusion_set_view")
+
+    def set_color(self, index: int, bgr):
+        """bgr: (h, w, 3) uint8 in cv2.imread(IMREAD_COLOR) order, at the depth map's size (RunFusion's colour, cpp:322)."""
+        b = np.ascontiguousarray(bgr, dtype=np.uint8)
+        assert b.ndim == 3 and b.shape[2] == 3
+        _ck(lib().mpmvs_fusion_set_color(self.h, int(index), b.ctypes.data), "fusion_set_color")
 
     def set_sky_mask(self, index: int, sky):
         """sky [h][w] uint8, > 0 = sky (skymask_refine.jpg): masked when that view's turn comes (PatchMatch.cpp:385-388)."""

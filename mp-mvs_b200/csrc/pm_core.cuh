@@ -1,9 +1,9 @@
 // pm_core.cuh -- per-pixel arithmetic of the PatchMatch path, written once for the sm_100a kernels.
 //
 // Behavioural spec: /root/reference/src/PatchMatch.cu ("cu:NNN" below). This is not a transcription:
-//   * everything that depends only on (pixel, scale) -- the 36 bilateral weights of the window, the weighted
-//     reference mean/variance -- is computed once per pixel per sweep (pm_ref_stats, weights kept in a per-thread
-//     shared-memory table), not once per (hypothesis, view) as the reference does (cu:355-414);
+//   * the reference side of the NCC -- the weighted reference mean/variance of the window -- depends only on (pixel,
+//     scale) and is computed once per pixel per sweep (pm_ref_stats), not once per (hypothesis, view) as the reference
+//     does (cu:355-414);
 //   * the reference window comes from a shared-memory tile (Ctx::ref), source samples from the texture
 //     unit (Ctx::src), source depths from plain global loads (Ctx::src_depth);
 //   * views with zero sampling weight are skipped where the reference multiplies their cost by 0
@@ -50,8 +50,21 @@
 #define PM_EARLY_OUT 1   // stop scoring a refinement proposal once it can no longer be accepted (result-identical)
 #endif
 #ifndef PM_WTAB
-#define PM_WTAB 1        // bilateral weights of a pixel's window: computed once per launch into a per-thread table (Ctx::wt)
-#endif                   // instead of once per tap of every NCC (result-identical: they depend on the reference window only)
+// 1: the 36 bilateral weights of a pixel's window are computed once per launch into a per-thread shared-memory table (Ctx::wt)
+// instead of once per tap of every NCC (result-identical: they depend on the reference window only). Measured on B200 and NOT
+// adopted: the table's 18 KB per block come out of the L1/TEX cache the source fetches live on, and the photometric Run() of
+// the exact arithmetic takes 404 ms with it against 354 ms without (profiles/r02_wtab_experiment.md).
+#define PM_WTAB 0
+#endif
+#ifndef PM_VIEW_MAJOR
+// 1: the 8 x (N-1) candidate costs of a pixel are evaluated view by view (all candidates against source 0, then source 1,
+// ...) instead of candidate by candidate: eight consecutive NCCs of a block then sample the SAME source image, whose warped
+// window stays in the L1/TEX cache. Result-identical (the costs are independent of one another).
+#define PM_VIEW_MAJOR 0
+#endif
+#ifndef PM_NCC_NOINLINE
+#define PM_NCC_NOINLINE 0   // 1: the 36-tap NCC is a real function (one copy in the instruction cache however many call sites)
+#endif
 #ifndef PM_EXACT
 #define PM_EXACT 0
 #endif
@@ -220,7 +233,18 @@ PM_HD void pm_rng_store(uint32_t* g, int idx, const PmRng& s) {
 }
 
 // ------------------------------------------------------------------------------------------------ geometry
-PM_HD float pm_dot3(const pm_f4& a, const pm_f4& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// Vec3DotVec3, cu:9-12. Exact arithmetic: nvcc contracts the reference's `a.x*b.x + a.y*b.y + a.z*b.z` to
+// FFMA(az, bz, FFMA(ax, bx, FMUL(ay, by))) in every inlined copy (the MIDDLE product is the rounded one: SASS of oracle/_ref,
+// all ten acos sites of Black/RedPixelUpdate). Left to the compiler OUR copies do not all come out that way (the one in the
+// refinement rounded the first product), and one ulp in |n|^2 decides whether acos(n . n) is 0 or NaN where a hypothesis
+// carries the prior's own normal -- 0.015 % of the pixels of a full-size planar-prior sweep. Pinned.
+PM_HD float pm_dot3(const pm_f4& a, const pm_f4& b) {
+#if PM_EXACT && defined(__CUDA_ARCH__)
+    return __fmaf_rn(a.z, b.z, __fmaf_rn(a.x, b.x, __fmul_rn(a.y, b.y)));
+#else
+    return a.x * b.x + a.y * b.y + a.z * b.z;
+#endif
+}
 
 // ComputeDepthfromPlaneHypothesis, cu:84-87.
 // K[0] / K[4] is formed on the device by the reference: under --use_fast_math an approximate division (x * rcp(x) is
@@ -598,6 +622,18 @@ PM_HD float pm_ncc(const Ctx& c, const PmFrame& F, const PmRefStats& st, int v, 
 #endif
 }
 
+#if PM_NCC_NOINLINE && defined(__CUDACC__)
+template <int SCALE, class Ctx>
+__device__ __noinline__ float pm_ncc_call(const Ctx& c, const PmFrame& F, const PmRefStats& st, int v, const PmHyp& hyp, int x, int y, uint32_t& nexec) {
+    return pm_ncc<SCALE>(c, F, st, v, hyp, x, y, nexec);
+}
+#else
+template <int SCALE, class Ctx>
+PM_HD float pm_ncc_call(const Ctx& c, const PmFrame& F, const PmRefStats& st, int v, const PmHyp& hyp, int x, int y, uint32_t& nexec) {
+    return pm_ncc<SCALE>(c, F, st, v, hyp, x, y, nexec);
+}
+#endif
+
 // ComputeGeomConsistencyCost, cu:617-640.
 #if PM_EXACT
 // BackProjectPoint2W, cu:582-603, and ProjectPoint, cu:605-615, on a camera given as (K, R, t, C)
@@ -782,8 +818,20 @@ PM_HD void pm_sweep_pixel(const Ctx& c, const PmFrame& F, const PmState& S, int 
     pm_f4 rand_n = cur, pert_n = cur, base_n = cur, prior_pl = cur;
     bool has_prior = false;
 
+#if PM_VIEW_MAJOR
+    // ---- candidate cost table, view-major (cu:798-819 evaluates it candidate-major; the entries are independent)
 #pragma unroll 1
-    for (int h = 0; h < 14; ++h) {
+    for (int v = 0; v < nsrc; ++v) {
+#pragma unroll 1
+        for (int h = 0; h < 8; ++h) {
+            if (!((flags >> h) & 1u)) continue;
+            const PmHyp hyp = pm_hyp(F, S.planes[pos[h]], x, y);
+            ca(h, v) = pm_ncc_call<SCALE>(c, F, st, v, hyp, x, y, nexec);
+        }
+    }
+#endif
+#pragma unroll 1
+    for (int h = PM_VIEW_MAJOR ? 8 : 0; h < 14; ++h) {
         if (h == 8) {
             // ---- view selection (cu:821-878)
             uint32_t nb[4];  // neighbour masks: up / down / left / right, gated by the flags of regions 0..3 (cu:824-830)
@@ -958,7 +1006,7 @@ PM_HD void pm_sweep_pixel(const Ctx& c, const PmFrame& F, const PmState& S, int 
         for (uint32_t m = mask; m; m &= m - 1) {
             const int v = pm_ffs(m) - 1;
 #endif
-            const float cst = pm_ncc<SCALE>(c, F, st, v, hyp, x, y, nexec);
+            const float cst = pm_ncc_call<SCALE>(c, F, st, v, hyp, x, y, nexec);
             if (h < 8) {
                 ca(h, v) = cst;
             } else {

@@ -26,6 +26,7 @@ struct FusionView {
     const float* depth;          // [H][W]
     const float* normal;         // [H][W][3] world frame
     const unsigned char* gray;   // [H][W]
+    const unsigned char* bgr;    // optional [H][W][3], cv::imread(IMREAD_COLOR) order (cpp:322): the colour the reference averages
     unsigned char* mask_prev;    // masks as of the start of the current image's launch
     unsigned char* mask_next;    // masks set during the current launch
     const unsigned char* sky;    // optional [H][W], > 0 = sky (skymask_refine, cpp:358-373)
@@ -64,7 +65,9 @@ __global__ void __launch_bounds__(256) pm_fuse_kernel(const FusionView* views, i
     float PX[3];
     world_point((float)c, (float)r, ref_depth, R.cam, PX);
     float sumP[3] = {PX[0], PX[1], PX[2]}, sumN[3] = {rn[0], rn[1], rn[2]};
-    float sumC = (float)R.gray[idx];
+    // consistent_Color (cpp:399,443-445): B, G, R of the colour image; a view without one contributes its grey level thrice
+    float sumC[3];
+    for (int k = 0; k < 3; ++k) sumC[k] = R.bgr ? (float)R.bgr[3 * idx + k] : (float)R.gray[idx];
     int num_consistent = 0;
     float dyn = 0.f;
     int used[MPMVS_MAX_VIEWS];
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(256) pm_fuse_kernel(const FusionView* views, i
         if (angle < 0.174533f) {
             used[j] = (int)sidx;
             for (int k = 0; k < 3; ++k) { sumP[k] += TX[k]; sumN[k] += sn[k]; }
-            sumC += (float)S.gray[sidx];
+            for (int k = 0; k < 3; ++k) sumC[k] += S.bgr ? (float)S.bgr[3 * sidx + k] : (float)S.gray[sidx];
             dyn += expf(-(reproj + 200 * rel + angle * 10));             // cpp:444-446
             ++num_consistent;
         }
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(256) pm_fuse_kernel(const FusionView* views, i
     if (!ok) return;
     FusedPoint p;
     const float inv = 1.0f / (num_consistent + 1.0f);
-    for (int k = 0; k < 3; ++k) { p.coord[k] = sumP[k] * inv; p.normal[k] = sumN[k] * inv; p.color[k] = sumC * inv; }
+    for (int k = 0; k < 3; ++k) { p.coord[k] = sumP[k] * inv; p.normal[k] = sumN[k] * inv; p.color[k] = sumC[k] * inv; }
     out[idx] = p;
     keep[idx] = 1;
     for (int j = 1; j < num_ngb; ++j)
@@ -181,6 +184,20 @@ int mpmvs_fusion_set_view(mpmvs_fusion* f, int index, const mpmvs_camera* cam, c
     FCK(cudaMemset(m0, 0, wh));
     FCK(cudaMemset(m1, 0, wh));
     v.cam = *cam; v.depth = dd; v.normal = dn; v.gray = dg; v.mask_prev = m0; v.mask_next = m1; v.W = cam->width; v.H = cam->height;
+    return MPMVS_OK;
+}
+
+// bgr [h][w][3] uint8 (cv::imread(IMREAD_COLOR) channel order, at the size of the depth map): the colour RunFusion averages
+// per point (cpp:322,399,443-445). Optional: a view without it contributes its grey level to all three channels.
+int mpmvs_fusion_set_color(mpmvs_fusion* f, int index, const uint8_t* bgr) {
+    if (!f || index < 0 || index >= f->n || !bgr) return MPMVS_E_ARG;
+    FusionView& v = f->hviews[index];
+    if (!v.W) return MPMVS_E_ARG;    // mpmvs_fusion_set_view first
+    FCK(cudaSetDevice(f->device));
+    const size_t bytes = (size_t)v.W * v.H * 3;
+    unsigned char* d = const_cast<unsigned char*>(v.bgr);
+    if (!d) { FCK(cudaMalloc((void**)&d, bytes)); f->owned.push_back(d); v.bgr = d; }
+    FCK(cudaMemcpy(d, bgr, bytes, cudaMemcpyHostToDevice));
     return MPMVS_OK;
 }
 

@@ -43,6 +43,19 @@ def load_image(folder: str, image_id: int, max_size: int):
     return out, nw / np.float32(w), nh / np.float32(h)
 
 
+def load_color(folder: str, image_id: int, shape):
+    """The colour image RunFusion reads (cv::imread(IMREAD_COLOR), PatchMatch.cpp:322) at the depth map's size (its
+    RescaleImageAndCamera resizes with INTER_LINEAR, cpp:341-345). None when the folder only has the grey .pgm sidecar."""
+    import cv2
+
+    bgr = cv2.imread(os.path.join(folder, f"{image_id:08d}.jpg"), cv2.IMREAD_COLOR)
+    if bgr is None:
+        return None
+    if bgr.shape[:2] != tuple(shape):
+        bgr = cv2.resize(bgr, (shape[1], shape[0]), interpolation=cv2.INTER_LINEAR)
+    return bgr
+
+
 def image_size(folder: str, image_id: int):
     """(width, height) of an image of the dense folder without decoding it: the PGM header of the sidecar, else the JPEG's
     SOF segment. Falls back to decoding."""
@@ -245,6 +258,9 @@ def main():
             cam = cams[i]
             cam.height, cam.width = d.shape
             fz.set_view(i, io_formats.pack_cameras([cam]), d, nrm, np.clip(np.rint(img), 0, 255).astype(np.uint8))
+            bgr = load_color(os.path.join(cfg["Input-folder"].rstrip("/"), "images"), i, d.shape)
+            if bgr is not None:
+                fz.set_color(i, bgr)                       # RunFusion averages B, G, R of the colour image (cpp:322,443-445)
             sky = load_sky_mask(out, i, d.shape) if sky_seg else None
             if sky is not None:
                 fz.set_sky_mask(i, sky)

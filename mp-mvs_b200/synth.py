@@ -416,3 +416,18 @@ def accuracy_at(depth, gt_depth, thresholds=(0.02, 0.05, 0.10)) -> List[float]:
     v = gt_depth > 0
     err = np.abs(np.asarray(depth, np.float64) - gt_depth)
     return [float(100.0 * ((err < t) & v).sum() / max(1, v.sum())) for t in thresholds]
+
+
+def accuracy_completeness_at(depth, cost, gt_depth, thresholds=(0.02, 0.05, 0.10), max_cost=0.5):
+    """Accuracy and completeness of one depth map against the rendered ground truth, the depth-map form of the two MVS
+    measures: a pixel is RECONSTRUCTED when its matching cost is below `max_cost` (the reference never marks a pixel
+    invalid, /root/reference/src/PatchMatch.cpp:610-618; the cost is what its fusion and its planar prior gate on);
+    accuracy(t)     = % of the reconstructed pixels that have ground truth and lie within t of it      (precision)
+    completeness(t) = % of the ground-truth pixels that are reconstructed and lie within t of the truth  (recall).
+    Scene units are metres, so t = 0.02 / 0.05 / 0.10 are the north star's 2 / 5 / 10 cm. Returns (accuracy, completeness)."""
+    v = np.asarray(gt_depth) > 0
+    rec = (np.asarray(cost) < max_cost) & np.isfinite(depth)
+    err = np.abs(np.asarray(depth, np.float64) - gt_depth)
+    acc = [float(100.0 * ((err < t) & v & rec).sum() / max(1, (v & rec).sum())) for t in thresholds]
+    comp = [float(100.0 * ((err < t) & v & rec).sum() / max(1, v.sum())) for t in thresholds]
+    return acc, comp

@@ -40,6 +40,8 @@ def fuse(cams, depths, normals, grays, src_lists, dynamic=True, sky=None):
     sky: optional per-image uint8 masks (> 0 = sky, None = no mask): masked when the image's turn comes (cpp:385-388).
     Returns (n, 9) float32 points in the kernel's order (images in order, raster order inside an image)."""
     n = len(cams)
+    # colour: (h, w, 3) B, G, R images as RunFusion reads them (cpp:322), or grey (h, w) images counted thrice
+    grays = [g.astype(np.float32) if g.ndim == 3 else np.repeat(g.astype(np.float32)[..., None], 3, -1) for g in grays]
     masks = [np.zeros(d.shape, bool) for d in depths]
     out = []
     for i in range(n):
@@ -53,7 +55,7 @@ def fuse(cams, depths, normals, grays, src_lists, dynamic=True, sky=None):
         alive = (~masks[i]) & (ref_depth > 0)
         PX = _world(xs, ys, ref_depth, cams[i])
         rn = normals[i].astype(np.float32)
-        sumP, sumN, sumC = PX.copy(), rn.copy(), grays[i].astype(np.float32).copy()
+        sumP, sumN, sumC = PX.copy(), rn.copy(), grays[i].copy()
         numc = np.zeros((h, w), np.int32)
         dyn = np.zeros((h, w), np.float32)
         num_ngb = len(src_lists[i])
@@ -90,14 +92,14 @@ def fuse(cams, depths, normals, grays, src_lists, dynamic=True, sky=None):
             ok = act & (reproj < 2.0) & (rel < 0.01) & (ang < np.float32(0.174533))
             sumP[ok] += TX[ok]
             sumN[ok] += sn[ok]
-            sumC[ok] += grays[s][src_r, src_c].astype(np.float32)[ok]
+            sumC[ok] += grays[s][src_r, src_c][ok]
             with np.errstate(all="ignore"):
                 dyn[ok] += np.exp(-(reproj + 200 * rel + ang * 10)).astype(np.float32)[ok]
             numc[ok] += 1
             used[j] = (ok, src_r, src_c, s)
         keep = alive & ((numc >= 1) & (dyn > np.float32(0.3) * numc) if dynamic else (numc >= 2))
         inv = (1.0 / (numc + 1.0)).astype(np.float32)
-        pts = np.concatenate([sumP * inv[..., None], sumN * inv[..., None], np.repeat((sumC * inv)[..., None], 3, -1)], -1)
+        pts = np.concatenate([sumP * inv[..., None], sumN * inv[..., None], sumC * inv[..., None]], -1)
         out.append(pts[keep])
         for j, (ok, src_r, src_c, s) in used.items():
             m = ok & keep

@@ -70,6 +70,33 @@ def test_gpu_fusion_matches_restatement(dynamic):
 
 
 @pytest.mark.gpu
+def test_gpu_fusion_averages_the_colour_image():
+    """RunFusion reads the images with IMREAD_COLOR and averages B, G, R per point (PatchMatch.cpp:322,399,443-445):
+    mpmvs_fusion_set_color gives the GPU fusion the colour image; without it the grey level fills all three channels."""
+    import fusion_oracle
+
+    from mpmvs_b200 import capi
+
+    sc, depths, normals, lists = noisy_scene()
+    cams = io_formats.pack_cameras(sc.cams)
+    bgr = [np.stack([g, 255 - g, g // 2], -1).astype(np.uint8) for g in sc.images]
+    want = fusion_oracle.fuse(cams, depths, normals, bgr, lists, dynamic=True)
+    f = capi.Fusion(0, sc.num_views)
+    for i in range(sc.num_views):
+        f.set_view(i, cams[i:i + 1], depths[i], normals[i], sc.images[i])
+        f.set_color(i, bgr[i])
+    got, _ = f.run(lists, True)
+    f.destroy()
+    assert abs(len(got) - len(want)) <= 0.003 * len(want)
+    # colour statistics: the three channels differ from one another and agree with the restatement's
+    assert np.abs(got[:, 6:9].mean(0) - want[:, 6:9].mean(0)).max() < 0.5
+    assert abs(got[:, 6].mean() - got[:, 7].mean()) > 5.0
+    key = lambda p: set(map(tuple, np.round(np.concatenate([p[:, :3] * 1e4, p[:, 6:9]], 1)).astype(np.int64)))  # noqa: E731
+    a, b = key(got), key(want)
+    assert len(a & b) > 0.98 * len(b), (len(a & b), len(b))
+
+
+@pytest.mark.gpu
 def test_gpu_fusion_vs_sequential_host(tmp_path):
     """Against the reference's order (C++ RunFusion in mpmvs_main, run on the PatchMatch results it produced itself)."""
     from test_cpp_host import MAIN, build_main, write_scene

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "mp-mvs_b200", "csrc")
 OUT = os.path.join(ROOT, "mp-mvs_b200", "variants")
 
-# "default" = the in-tree defaults (PM_BH=4, PM_MIN_BLOCKS=3, PM_CA_SMEM=1, PM_UNIFORM_VIEWS=1, PM_EARLY_OUT=1, PM_WTAB=1)
+# "default" = the in-tree defaults (PM_BH=4, PM_MIN_BLOCKS=3, PM_CA_SMEM=1, PM_UNIFORM_VIEWS=1, PM_EARLY_OUT=1, PM_WTAB=0)
 VARIANTS = {
     "default": [],
     "noeo": ["-DPM_EARLY_OUT=0"],
@@ -20,9 +20,11 @@ VARIANTS = {
     "mb4": ["-DPM_MIN_BLOCKS=4"],
     "bh2mb6": ["-DPM_BH=2", "-DPM_MIN_BLOCKS=6"],
     "bh8mb1": ["-DPM_BH=8", "-DPM_MIN_BLOCKS=1"],
-    "nowtab": ["-DPM_WTAB=0"],                       # bilateral weights recomputed per tap instead of the shared-memory table
-    "nowtab_mb2": ["-DPM_WTAB=0", "-DPM_MIN_BLOCKS=2"],
-    "wtab_mb2": ["-DPM_MIN_BLOCKS=2"],
+    "vm": ["-DPM_VIEW_MAJOR=1"],                      # candidate costs view by view (two inlined copies of the NCC)
+    "vmni": ["-DPM_VIEW_MAJOR=1", "-DPM_NCC_NOINLINE=1"],   # ... with the NCC as a real function (one copy)
+    "ni": ["-DPM_NCC_NOINLINE=1"],
+    "wtab": ["-DPM_WTAB=1"],                         # bilateral weights from a per-thread shared-memory table (measured: slower)
+    "wtab_mb2": ["-DPM_WTAB=1", "-DPM_MIN_BLOCKS=2"],
 }
 
 
