@@ -71,6 +71,9 @@ def _canon(e):
     if k == "abs":
         s, _ = _canon(e[1])
         return "abs(" + s + ")", False
+    if k == "i2f" and e[1][0] == "leaf":
+        return "x", False       # a converted integer register is a leaf like any other (the compiler keeps some conversions in
+                                # registers across code this straight-line executor cannot follow, and they then show up as leaves)
     if k in ("rcp", "sqrt", "ex2", "i2f"):
         return k + "(" + canon(e[1]) + ")", False
     if k == "FMUL":
