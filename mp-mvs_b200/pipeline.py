@@ -56,6 +56,11 @@ class PipelineConfig:
     tex_format: Optional[int] = None  # capi.TEX_*; None = float32 with the exact arithmetic (what its bit-identity needs),
                                       # 8-bit with the fast one (views are 8-bit grey levels as decoded from the JPEGs)
     keep_normals: bool = True
+    order: str = "jacobi"             # "jacobi": every image of a geometric pass reads the maps of the previous pass (any number of
+                                      # GPUs, results independent of the sharding); "gauss_seidel": the reference's own order -- images
+                                      # one after the other, each reading the maps images before it already updated in this pass
+                                      # (PatchMatch.cpp:620-633 overwrites depths.dmb in place) -- one GPU only
+    keep_priors: bool = False         # tests: keep a host copy of every prior (planes, mask) the planar-prior stage builds
 
 
 @dataclass
@@ -110,6 +115,8 @@ class CudaEngine:
         self.pm = capi.PatchMatch(device, stream=stream).set_arithmetic(arithmetic)
         self.pm.set_problem_cached(cache, list(ids), cams_packed)
         self.prior_stats = None
+        self.keep_prior = False
+        self.saved_priors = []      # (planes, mask) of every planar-prior stage of this image, in pass order (keep_prior)
 
     def process(self, seed: int, geom: bool, planar: bool, src_depth_ptrs: Optional[Sequence[int]] = None, turn=None):
         """The compute of one ProcessProblem(geom, planar) call (PatchMatch.cpp:516-609) on the resident state:
@@ -128,6 +135,8 @@ class CudaEngine:
             pm.set_planar_prior_params()
             pm.set_geom_consistency_params(False, True)
             self.prior_stats = pm.build_prior()             # blocks this host thread only
+            if self.keep_prior:
+                self.saved_priors.append(pm.get_prior())
             with (turn or _NoTurn()):
                 pm.run_async(seed ^ 0x5DEECE66D)
                 if turn is not None:
@@ -219,6 +228,7 @@ class DensePipeline:
             if self.engine_factory is None:
                 self.engines[ref] = CudaEngine(self.device, self.cache, ids, packed, self.cfg.arithmetic,
                                                self.streams[k % len(self.streams)].cuda_stream)
+                self.engines[ref].keep_prior = self.cfg.keep_priors
             else:
                 self.engines[ref] = self.engine_factory(ids, [self.images[i] for i in ids], packed)
         if self.cfg.geom_iterations > 0:
@@ -308,7 +318,17 @@ class DensePipeline:
                 self.engines[ref].process(seed, False, planar, **extra)
 
         t0 = self._tick()
-        if self.cfg.in_flight > 1 and len(self.my_refs) > 1:
+        if geom and self.cfg.order == "gauss_seidel":
+            # the reference's order (main.cpp:35-40 + PatchMatch.cpp:620-633): one image after the other, its fresh depth map
+            # replaces the old one at once, so the images after it in this pass already read it
+            if self.world != 1:
+                raise ValueError("the Gauss-Seidel order is sequential over ALL reference images: one GPU only")
+            for ref in self.my_refs:
+                one(ref)
+                self.engines[ref].synchronize()
+                self.engines[ref].export_depth(prev[self.slot[ref]])
+                self.engines[ref].synchronize()
+        elif self.cfg.in_flight > 1 and len(self.my_refs) > 1:
             with ThreadPoolExecutor(self.cfg.in_flight) as ex:
                 list(ex.map(one, self.my_refs))
         else:
@@ -332,7 +352,7 @@ class DensePipeline:
             planar = cfg.geom_planar_prior and g != cfg.geom_iterations - 1
             st = PassStats(f"geometric {g}" + (" + planar prior" if planar else ""), n_refs=len(self.my_refs))
             self._run_pass(st, 1 + g, True, planar, self.gathered)
-            if g + 1 < cfg.geom_iterations:
+            if g + 1 < cfg.geom_iterations and cfg.order != "gauss_seidel":      # Gauss-Seidel updated `gathered` in place
                 self._exchange(st)
             self.stats.append(st)
         return self.stats

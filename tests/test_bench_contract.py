@@ -71,7 +71,8 @@ def test_clock_sampler_without_nvidia_smi(monkeypatch):
 
 def test_roofline_constants():
     assert bench.TAPS_PER_NCC == 36 and bench.BYTES_PER_TAP == 16 and bench.N_SM == 148 and bench.TEX_PER_CLK_SM == 4
-    assert bench.ncu_traffic("eth3d") == pytest.approx(684e6)
+    assert bench.ncu_traffic("eth3d") == pytest.approx(920.5e6, rel=1e-3)          # exact arithmetic, float32 views
+    assert bench.ncu_traffic("eth3d", "fast", "u8") == pytest.approx(684e6)
     assert bench.ncu_traffic("dtu") is None
 
 

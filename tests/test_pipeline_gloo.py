@@ -114,6 +114,39 @@ def test_two_ranks_match_one_rank(tmp_path, oracle_cpu):
     assert any(not np.array_equal(photo[r][0], single[r][0]) for r in single)
 
 
+def test_gauss_seidel_order_is_the_references_in_place_exchange(oracle_cpu):
+    """PipelineConfig.order = "gauss_seidel" (one GPU): inside a geometric pass the images run one after the other and each
+    reads the depth maps the images before it have ALREADY written in this pass -- what the reference does through its
+    depths.dmb files (main.cpp:35-40, PatchMatch.cpp:620-633, 934-950). Checked against a plain sequential loop."""
+    entries, cams, images = make_inputs()
+    cfg = pipeline.PipelineConfig(geom_iterations=2, max_src=2, seed=77, order="gauss_seidel")
+    p = pipeline.DensePipeline(entries, cams, images, cfg, engine_factory=lambda ids, imgs, packed: OracleEngine(ids, imgs, packed),
+                               torch_device=torch.device("cpu"))
+    p.run()
+    got = p.results()
+    p.destroy()
+    # the same schedule by hand
+    eng = {e.ref_id: OracleEngine(e.src_ids[:3], [images[i] for i in e.src_ids[:3]], io_formats.pack_cameras([cams[i] for i in e.src_ids[:3]]))
+           for e in entries}
+    for r in sorted(eng):
+        eng[r].process(pipeline.stage_seed(77, r, 0), False, False)
+    maps = {r: torch.from_numpy(eng[r].result()[0][..., 3].copy()) for r in eng}
+    for g in range(2):
+        for r in sorted(eng):
+            srcs = [e for e in entries if e.ref_id == r][0].src_ids[1:3]
+            eng[r].process(pipeline.stage_seed(77, r, 1 + g), True, False, [maps[j] for j in srcs])
+            maps[r] = torch.from_numpy(eng[r].result()[0][..., 3].copy())        # in place: the next image sees it
+    for r in sorted(eng):
+        np.testing.assert_array_equal(got[r][0], eng[r].result()[0])
+        np.testing.assert_array_equal(got[r][1], eng[r].result()[1])
+        eng[r].destroy()
+    jac = run_pipeline(0, 1)
+    assert any(not np.array_equal(jac[r][0], got[r][0]) for r in got)          # and it is not the Jacobi result
+    with pytest.raises(ValueError):
+        pipeline.DensePipeline(entries, cams, images, cfg, rank=0, world=2, engine_factory=lambda *a: None,
+                               torch_device=torch.device("cpu"))._run_pass(pipeline.PassStats("x"), 1, True, False, None)
+
+
 def test_gpu_turn_is_fifo():
     """pipeline.GpuTurn: whole Run()s take turns on a GPU in the order the host threads asked for them."""
     import threading
