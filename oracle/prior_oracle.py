@@ -65,8 +65,19 @@ def delaunay_cv(points, w, h):
     return np.array(tris, dtype=np.int32).reshape(-1, 3, 2)
 
 
+def solve_z(A):
+    """cv::SVD::solveZ (modules/core/src/lapack.cpp: SVD svd(m, rows >= cols ? 0 : FULL_UV); dst = last row of vt) on a
+    float32 matrix, through the SAME library the reference links (cv2 = OpenCV's Python binding; SVDecomp is cv::SVD::compute):
+    the third-party arithmetic of GetPriorPlaneParams comes from the dependency itself, not from a restatement."""
+    import cv2
+
+    A = np.ascontiguousarray(A, np.float32)
+    _, _, vt = cv2.SVDecomp(A, flags=0 if A.shape[0] >= A.shape[1] else cv2.SVD_FULL_UV)
+    return vt[-1].astype(np.float32)
+
+
 def plane_from_triangle(tri, depth, K):
-    """GetPriorPlaneParams, PatchMatch.cpp:723-755: null vector of the 3x4 system [X 1] (cv::SVD::solveZ)."""
+    """GetPriorPlaneParams, PatchMatch.cpp:723-755: null vector of the 3x4 system [X 1] (cv::SVD::solveZ, float32)."""
     A = np.zeros((3, 4), np.float32)
     for k, (x, y) in enumerate(tri):
         d = np.float32(depth[y, x])
@@ -74,8 +85,7 @@ def plane_from_triangle(tri, depth, K):
         A[k, 1] = d * (np.float32(y) - K[1, 2]) / K[1, 1]
         A[k, 2] = d
         A[k, 3] = 1.0
-    _, _, vt = np.linalg.svd(A.astype(np.float64))
-    n4 = vt[-1].astype(np.float32)
+    n4 = solve_z(A)
     norm2 = np.float32(np.sqrt(np.float64(n4[0]) ** 2 + np.float64(n4[1]) ** 2 + np.float64(n4[2]) ** 2))
     if n4[3] < 0:
         norm2 = -norm2
