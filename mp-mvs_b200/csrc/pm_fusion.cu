@@ -222,12 +222,22 @@ int mpmvs_fusion_run(mpmvs_fusion* f, const int* src_lists, int max_list, int us
     FCK(cudaMemcpy(f->dviews, f->hviews.data(), sizeof(FusionView) * f->n, cudaMemcpyHostToDevice));
     size_t total = 0, max_wh = 0;
     for (const FusionView& v : f->hviews) { const size_t wh = (size_t)v.W * v.H; total += wh; max_wh = wh > max_wh ? wh : max_wh; }
-    if (total > f->cap_points) {
+    // The point buffer grows with the points actually fused (typically a small fraction of the pixels), not with the pixel
+    // count of the scene: 36 B per pixel of every view would be 23 GB for 96 views of 3200 x 2130.
+    auto reserve = [&](size_t need) -> int {
+        if (need <= f->cap_points) return MPMVS_OK;
+        const size_t cap = need > 2 * f->cap_points ? need : 2 * f->cap_points;
+        FusedPoint* grown = nullptr;
+        FCK(cudaMalloc((void**)&grown, cap * sizeof(FusedPoint)));
+        if (f->n_points) FCK(cudaMemcpy(grown, f->d_points, f->n_points * sizeof(FusedPoint), cudaMemcpyDeviceToDevice));
         cudaFree(f->d_points);
-        f->d_points = nullptr;
-        FCK(cudaMalloc((void**)&f->d_points, total * sizeof(FusedPoint)));
-        f->cap_points = total;
-    }
+        f->d_points = grown;
+        f->cap_points = cap;
+        return MPMVS_OK;
+    };
+    (void)total;
+    f->n_points = 0;
+    { int rc0 = reserve(2 * max_wh); if (rc0) return rc0; }
     struct Temps {                       // freed on every return path
         FusedPoint* tmp = nullptr;
         unsigned char* keep = nullptr;
@@ -252,7 +262,6 @@ int mpmvs_fusion_run(mpmvs_fusion* f, const int* src_lists, int max_list, int us
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    f->n_points = 0;
     int rc = MPMVS_OK;
     for (int i = 0; i < f->n && rc == MPMVS_OK; ++i) {
         const FusionView& v = f->hviews[i];
@@ -261,6 +270,8 @@ int mpmvs_fusion_run(mpmvs_fusion* f, const int* src_lists, int max_list, int us
         int num_ngb = 0;
         while (num_ngb < max_list && row[num_ngb] != -2) ++num_ngb;
         const size_t wh = (size_t)v.W * v.H;
+        rc = reserve(f->n_points + wh);               // worst case: every pixel of this image fuses
+        if (rc) break;
         if (v.sky) pm_mask_sky_kernel<<<(unsigned)((wh + 255) / 256), 256>>>(v.mask_prev, v.mask_next, v.sky, wh);
         pm_fuse_kernel<<<dim3((v.W + 31) / 32, (v.H + 7) / 8), dim3(32, 8)>>>(f->dviews, i, d_src + (size_t)i * max_list, num_ngb,
                                                                              use_dynamic_consistency ? 1 : 0, tmp, keep);
