@@ -113,6 +113,7 @@ def lib() -> C.CDLL:
         "mpmvs_set_arithmetic": [vp, i],
         "mpmvs_get_arithmetic": [vp, C.POINTER(i)],
         "mpmvs_default_arithmetic": [],
+        "mpmvs_selftest_ex2_monotone": [i, C.POINTER(u64)],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -137,6 +138,13 @@ class PriorStats(C.Structure):
 def build_flavor() -> str:
     """What the loaded library holds: "exact+fast" (both arithmetics, chosen per handle at run time)."""
     return lib().mpmvs_build_flavor().decode()
+
+
+def selftest_ex2_monotone(device: int = 0) -> int:
+    """Adjacent float pairs in [-160, -0] for which MUFU.EX2 is not monotone (0 expected; see mpmvs_selftest_ex2_monotone)."""
+    v = C.c_uint64()
+    _ck(lib().mpmvs_selftest_ex2_monotone(int(device), C.byref(v)), "selftest_ex2_monotone")
+    return int(v.value)
 
 
 def default_arithmetic() -> str:

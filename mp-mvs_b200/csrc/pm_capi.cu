@@ -1019,6 +1019,22 @@ int mpmvs_get_prior(mpmvs_problem* p, float* prior_planes4_host, uint32_t* mask_
     return MPMVS_OK;
 }
 
+int mpmvs_selftest_ex2_monotone(int device, uint64_t* violations) {
+    if (!violations) return MPMVS_E_ARG;
+    int rc = ensure_device(device);
+    if (rc) return rc;
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc((void**)&d, sizeof(*d)));
+    cudaError_t e = cudaMemset(d, 0, sizeof(*d));
+    if (e == cudaSuccess) e = pm_launch_ex2_monotone(-160.0f, d, 0);
+    unsigned long long v = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&v, d, sizeof(v), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return (int)e;
+    *violations = v;
+    return MPMVS_OK;
+}
+
 int mpmvs_uniform_stream(uint64_t seed, int x, int y, int n, float* out_host) {
     if (!out_host || n <= 0) return MPMVS_E_ARG;
     int rc = ensure_device(0);

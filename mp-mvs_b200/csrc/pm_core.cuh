@@ -56,6 +56,14 @@
 // the exact arithmetic takes 404 ms with it against 354 ms without (profiles/r02_wtab_experiment.md).
 #define PM_WTAB 0
 #endif
+#ifndef PM_PRIOR_EARLY_OUT
+// The same for proposals scored under the planar prior (cu:696-711): their acceptance test `exp(-tc^2 / beta) * prior >
+// restricted_cost` is monotone in the running cost too -- every step of the chain (FMUL by a positive constant, FMUL(t, -t)
+// for t >= 0, MUFU.EX2, FMUL by prior >= 0.5) is non-increasing in tc, and rounding keeps weak monotonicity -- so a proposal
+// whose PARTIAL cost already fails it can never pass. MUFU.EX2's monotonicity over the whole argument range is a GPU test
+// (mpmvs_selftest_ex2_monotone, tests/test_zz_fidelity_build_gpu.py). A NaN prior fails at the first view, as it does at the end.
+#define PM_PRIOR_EARLY_OUT 1
+#endif
 #ifndef PM_VIEW_MAJOR
 // 1: the 8 x (N-1) candidate costs of a pixel are evaluated view by view (all candidates against source 0, then source 1,
 // ...) instead of candidate by candidate: eight consecutive NCCs of a block then sample the SAME source image, whose warped
@@ -996,6 +1004,12 @@ PM_HD void pm_sweep_pixel(const Ctx& c, const PmFrame& F, const PmState& S, int 
         }
         const PmHyp hyp = pm_hyp(F, tp, x, y);
         float tc = 0.f, tg = 0.f;
+        float prior_f = 0.f;       // the prior factor of a refinement proposal (cu:696-700): known before its views are scored
+        if (h > 8 && has_prior) {
+            const float dd = hd - depth_prior;
+            const float ad = acosf(pm_dot3(prior_pl, tp));
+            prior_f = 0.5f + pm_exp(-dd * dd / two_ds2) * pm_exp(-ad * ad / two_as2);
+        }
 #pragma unroll 1
 #if PM_UNIFORM_VIEWS
         // every lane of a warp walks the views in the same order (lanes that do not need view v idle through it), so
@@ -1023,6 +1037,12 @@ PM_HD void pm_sweep_pixel(const Ctx& c, const PmFrame& F, const PmState& S, int 
                 // Costs are >= 0 and summed in the reference's order, so the running sum only grows: once it fails the
                 // acceptance test `tc / wnorm < cost_now` (cu:713) the remaining views cannot rescue the proposal.
                 if (h > 8 && !has_prior && !(tc / wnorm < cost_now)) break;
+#if PM_PRIOR_EARLY_OUT
+                if (h > 8 && has_prior) {
+                    const float t = tc / wnorm;
+                    if (!(pm_exp(-t * t / 0.18f) * prior_f > restricted_cost)) break;
+                }
+#endif
 #endif
             }
         }
@@ -1036,10 +1056,7 @@ PM_HD void pm_sweep_pixel(const Ctx& c, const PmFrame& F, const PmState& S, int 
             const float dbefore = pm_depth_from_plane(F, tp, x, y);
             const bool in_range = dbefore >= F.depth_min && dbefore <= F.depth_max;
             if (has_prior) {
-                const float dd = hd - depth_prior;
-                const float ad = acosf(pm_dot3(prior_pl, tp));
-                const float prior = 0.5f + pm_exp(-dd * dd / two_ds2) * pm_exp(-ad * ad / two_as2);
-                const float rtc = pm_exp(-tc * tc / 0.18f) * prior;
+                const float rtc = pm_exp(-tc * tc / 0.18f) * prior_f;
                 // QUIRK cu:707-710: restricted_cost is never refreshed after an accept
                 if (in_range && rtc > restricted_cost) { plane_now = tp; cost_now = tc; }
             } else if (in_range && tc < cost_now) {

@@ -24,6 +24,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <cstring>
 #include <type_traits>
 
 #include "pm_core.cuh"
@@ -406,6 +407,30 @@ __global__ void pm_literal_table_kernel(float one, float sigma_spatial, float si
 }  // namespace
 cudaError_t pm_launch_literal_table(float sigma_spatial, float sigma_color, float* out20_dev, cudaStream_t st) {
     pm_literal_table_kernel<<<1, 1, 0, st>>>(1.0f, sigma_spatial, sigma_color, out20_dev);
+    return cudaGetLastError();
+}
+
+namespace {
+// every float in [lo, hi]: ex2.approx.ftz(x) <= ex2.approx.ftz(next float above x)? (__expf = this instruction on x * log2 e)
+__global__ void pm_ex2_monotone_kernel(unsigned int bits_lo, unsigned int count, unsigned long long* violations) {
+    unsigned long long bad = 0;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        // negative floats: increasing bit pattern = decreasing value
+        const float x = __uint_as_float(bits_lo + i + 1u), x_up = __uint_as_float(bits_lo + i);
+        float a, b;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(x));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(b) : "f"(x_up));
+        bad += !(a <= b);
+    }
+    if (bad) atomicAdd(violations, bad);
+}
+}  // namespace
+cudaError_t pm_launch_ex2_monotone(float lo_negative, unsigned long long* violations_dev, cudaStream_t st) {
+    // all floats from -0.0f (0x80000000) down to lo_negative
+    unsigned int last;
+    memcpy(&last, &lo_negative, sizeof(last));
+    const unsigned int first = 0x80000000u;
+    pm_ex2_monotone_kernel<<<148 * 8, 256, 0, st>>>(first, last - first, violations_dev);
     return cudaGetLastError();
 }
 

@@ -48,6 +48,8 @@ cudaError_t pm_launch_export_depth(const pm_f4* planes, float* out, int W, int H
 cudaError_t pm_launch_uniform_stream(unsigned long long seed, int x, int y, int n, float* out, cudaStream_t st);
 // 18 tap distances + 2 reciprocals as the device evaluates them (pm_core.cuh: pm_literal_table) -> PmFrame::lit_*
 cudaError_t pm_launch_literal_table(float sigma_spatial, float sigma_color, float* out20_dev, cudaStream_t st);
+// MUFU.EX2 monotone over every float in [lo_negative, -0]? (the planar-prior early-out of pm_core.cuh relies on it)
+cudaError_t pm_launch_ex2_monotone(float lo_negative, unsigned long long* violations_dev, cudaStream_t st);
 // planar-prior stage (pm_prior.cu)
 cudaError_t pm_launch_pick_vertices(const float* costs, const float* geom, int W, int H, int geom_variant, short2* out_xy,
                                     unsigned char* out_n, cudaStream_t st);

@@ -35,6 +35,15 @@ def tool(name, *args, env=None):
     return json.loads(r.stdout.strip().splitlines()[-1])
 
 
+def test_ex2_is_monotone():
+    """The early-out of refinement proposals under the planar prior (PM_PRIOR_EARLY_OUT, pm_core.cuh) argues that the
+    acceptance test is monotone in the running cost; the one step of that chain that is hardware, MUFU.EX2, is checked here
+    for every float in [-160, -0] (1.13e9 adjacent pairs)."""
+    from mpmvs_b200 import capi
+
+    assert capi.selftest_ex2_monotone(0) == 0
+
+
 def test_exact_arithmetic_is_bit_identical_to_the_reference_photometric(oracle):
     """Started from the reference's state, EVERY half-sweep of a photometric Run() reproduces the reference's planes, costs and
     view masks bit for bit, and so does a whole same-seed Run() -- on the three parity cases."""
