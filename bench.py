@@ -27,8 +27,8 @@ metric = W*H*steps / seconds, summed over ranks.
            reference's operations one for one, float32 view storage, results bit-identical to the reference's kernels
            (tests/test_zz_fidelity_build_gpu.py). `arithmetic_fast` (N=1) reports the same step through the library's fast
            arithmetic with 8-bit view storage (statistically equal results) beside it; --no-fast-arm skips it.
-  cpu_baseline : the plain-C oracle port (oracle/pm_oracle.c, all host cores) on a centre crop of the same views
-           (photometric Run only: the port is the checker of the kernels, not a pipeline).
+  cpu_baseline : the plain-C oracle port (oracle/pm_oracle.c, all host cores) on a centre crop of the same views, one whole
+           step (photometric Run + planar-prior stage + prior Run).
   --impl reference : the reference's own CUDA path (oracle/_ref/libmpmvs_ref.so = /root/reference/src/PatchMatch.cu
            compiled in place for sm_100) on the same workload and step; its host planar-prior stage is the restatement in
            oracle/ (OpenCV Subdiv2D + plain C, one core). The reference has no CPU implementation of the kernels.
@@ -541,7 +541,7 @@ def cpu_baseline(prob, budget_s=20.0):
     import oracle_py
 
     W, H = prob["width"], prob["height"]
-    cw, ch = min(W, 448), min(H, 288)        # ~12 s of CPU work on the GPU box's 16 host cores
+    cw, ch = min(W, 352), min(H, 240)        # ~12 s of CPU work on the GPU box's 16 host cores
     x0, y0 = (W - cw) // 2, (H - ch) // 2
     # keep the sources whole (their warped windows must stay inside), crop only the reference: the oracle needs all
     # views at the size its camera says, so crop every view with the same window instead and shift cx, cy
@@ -551,15 +551,25 @@ def cpu_baseline(prob, budget_s=20.0):
         c["K"][2] -= x0
         c["K"][5] -= y0
         c["width"], c["height"] = cw, ch
+    import prior_oracle
+
     o = oracle_py.Oracle("cpu").set_problem(imgs, cams)
-    o.set_geom_consistency_params(False, False)
+    o.set_geom_consistency_params(False, True)
     cores = oracle_py.Oracle("cpu").lib.pmo_get_threads()
     t = time.time()
-    o.run(1)
+    o.run(1)                                                   # photometric Run()
+    planes, costs = o.result()
+    dmin, dmax = o.depth_range
+    prior, mask, _, _, _ = prior_oracle.build_prior_fast(planes, costs, cams["K"][0].reshape(3, 3), dmin, dmax)   # host prior stage
+    o.set_planar_prior_params()
+    o.set_geom_consistency_params(False, True)
+    o.set_prior(prior, mask)
+    o.run(2)                                                   # planar-prior Run()
     dt = time.time() - t
     o.destroy()
     return {"value": round(cw * ch / 1e6 / dt, 6), "unit": "Mpix/s", "cores": int(cores), "kind": "port",
-            "sample": f"centre crop {cw}x{ch} of all {len(imgs)} views, one full photometric Run() in {dt:.1f} s (oracle/pm_oracle.c, pthreads)"}
+            "sample": f"centre crop {cw}x{ch} of all {len(imgs)} views, one whole step (photometric Run + planar-prior stage + prior Run) in {dt:.1f} s "
+                      "(oracle/pm_oracle.c, pthreads; the reference has no CPU implementation of this path)"}
 
 
 def run_reference(args, prob):

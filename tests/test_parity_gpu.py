@@ -42,64 +42,80 @@ def state_of(g, prefix):
 
 
 # ------------------------------------------------------------------------------------------ (1) golden fixtures
+ARITH = ("exact", "fast")      # both arithmetics of the library; exact (the default) is checked with equality
+
+
+def who_of(arith):
+    return "gpu" if arith == "exact" else "gpu_fast"
+
+
+@pytest.mark.parametrize("arith", ARITH)
 @pytest.mark.parametrize("name", CASES)
-def test_golden_xorwow_and_maps(capi, name):
+def test_golden_xorwow_and_maps(capi, name, arith):
     g, c = gold(name), make_case(name)
     for (x, y), want in zip(((0, 0), (17, 5), (63, 47)), g["uniform"]):
         np.testing.assert_array_equal(capi.PatchMatch.uniform_stream(SEED, x, y, 64), want)
-    pm = capi.PatchMatch(0).set_problem(c["images"], c["cams"])
+    pm = capi.PatchMatch(0).set_arithmetic(arith).set_problem(c["images"], c["cams"])
     gt, rnd = gt_planes_cam(c["scene"], c["ref"]), random_planes(c)
     for s in (0, 1, 2):
-        check_cost_map(name, pm.ncc_map(gt, s), g[f"ncc_gt_s{s}"])
-        check_cost_map(name, pm.ncc_map(rnd, s), g[f"ncc_rnd_s{s}"])
+        check_cost_map(name, pm.ncc_map(gt, s), g[f"ncc_gt_s{s}"], exact=arith == "exact")
+        check_cost_map(name, pm.ncc_map(rnd, s), g[f"ncc_rnd_s{s}"], exact=arith == "exact")
     pm.set_geom_consistency_params(True, False)
     pm.set_src_depths(src_depths(c, 0.002))
-    assert frac_within(pm.geom_map(rnd), g["geom_rnd"], T_GEOM) >= 0.999
+    if arith == "exact":
+        np.testing.assert_array_equal(pm.geom_map(rnd), g["geom_rnd"])
+    else:
+        assert frac_within(pm.geom_map(rnd), g["geom_rnd"], T_GEOM) >= 0.999
     pm.destroy()
 
 
+@pytest.mark.parametrize("arith", ARITH)
 @pytest.mark.parametrize("name", CASES)
-def test_golden_stages(capi, name):
+def test_golden_stages(capi, name, arith):
     g, c = gold(name), make_case(name)
     h, w = g["init_costs"].shape
     black = colour_mask(h, w, 0)
-    pm = capi.PatchMatch(0).set_problem(c["images"], c["cams"])
+    GPU = who_of(arith)
+    pm = capi.PatchMatch(0).set_arithmetic(arith).set_problem(c["images"], c["cams"])
     pm.set_geom_consistency_params(False, False)
     pm.init_only(SEED)
-    check_state(name, pm.get_state(), state_of(g, "init"), "gpu", rng_digest=rng_hash, planes_exact=True)
+    check_state(name, pm.get_state(), state_of(g, "init"), GPU, rng_digest=rng_hash, planes_exact=True)
     st = pm.get_state()
     st.update(planes=g["init_planes"], costs=g["init_costs"], views=g["init_views"])
     pm.set_dev_state(st)
     pm.half_sweep(0, 0, 2)
-    check_state(name, pm.get_state(), state_of(g, "sweep"), "gpu", upd=black, rng_digest=rng_hash)
+    check_state(name, pm.get_state(), state_of(g, "sweep"), GPU, upd=black, rng_digest=rng_hash)
     # planar prior from the reference's photometric result
     pm.set_state(g["run_planes"], g["run_costs"])
     pm.set_planar_prior_params()
     pm.set_geom_consistency_params(False, True)
     pm.set_prior(*prior_planes(c))
     pm.init_only(SEED + 1)
-    check_state(name, pm.get_state(), state_of(g, "pinit"), "gpu", rng_digest=rng_hash, planes_exact=True)
+    check_state(name, pm.get_state(), state_of(g, "pinit"), GPU, rng_digest=rng_hash, planes_exact=True)
     st = pm.get_state()
     st.update(planes=g["pinit_planes"], costs=g["pinit_costs"], views=g["pinit_views"])
     pm.set_dev_state(st)
     pm.half_sweep(0, 0, 0)
-    check_state(name, pm.get_state(), state_of(g, "psweep"), "gpu", upd=black, rng_digest=rng_hash)
+    check_state(name, pm.get_state(), state_of(g, "psweep"), GPU, upd=black, rng_digest=rng_hash)
     pm.destroy()
     # geometric consistency
-    pm = capi.PatchMatch(0).set_problem(c["images"], c["cams"])
+    pm = capi.PatchMatch(0).set_arithmetic(arith).set_problem(c["images"], c["cams"])
     pm.set_geom_consistency_params(True, False)
     pm.set_src_depths(src_depths(c, 0.002))
     pm.set_state(*world_state_from_gt(c))
     pm.init_only(SEED + 2)
-    check_state(name, pm.get_state(), state_of(g, "ginit"), "gpu", rng_digest=rng_hash, planes_exact=True)
+    check_state(name, pm.get_state(), state_of(g, "ginit"), GPU, rng_digest=rng_hash, planes_exact=True)
     st = pm.get_state()
     st.update(planes=g["ginit_planes"], costs=g["ginit_costs"], views=g["ginit_views"])
     pm.set_dev_state(st)
     pm.half_sweep(0, 0, 0)
     got = pm.get_state()
-    check_state(name, got, state_of(g, "gsweep"), "gpu", upd=black, rng_digest=rng_hash)
+    check_state(name, got, state_of(g, "gsweep"), GPU, upd=black, rng_digest=rng_hash)
     same = np.all(got["planes"] == g["gsweep_planes"], -1)
-    assert np.abs(got["geom"] - g["gsweep_geom"])[same].mean() < 1e-3
+    if arith == "exact":
+        np.testing.assert_array_equal(got["geom"], g["gsweep_geom"])
+    else:
+        assert np.abs(got["geom"] - g["gsweep_geom"])[same].mean() < 1e-3
     pm.destroy()
 
 
@@ -109,18 +125,20 @@ def need_ref(oracle):
         pytest.skip("oracle/_ref/libmpmvs_ref.so not built on this box")
 
 
+@pytest.mark.parametrize("arith", ARITH)
 @pytest.mark.parametrize("name", CASES)
-def test_live_all_sweeps_vs_reference(capi, oracle, name):
+def test_live_all_sweeps_vs_reference(capi, oracle, name, arith):
     """Every half-sweep of a photometric Run, each started from the reference's own state."""
     need_ref(oracle)
     c = make_case(name)
-    pm = capi.PatchMatch(0).set_problem(c["images"], c["cams"])
+    GPU = who_of(arith)
+    pm = capi.PatchMatch(0).set_arithmetic(arith).set_problem(c["images"], c["cams"])
     ref = oracle.Oracle("ref").set_problem(c["images"], c["cams"])
     for o in (pm, ref):
         o.set_geom_consistency_params(False, False)
         o.init_only(SEED)
     sr = ref.get_state()
-    check_state(name, pm.get_state(), sr, "gpu", planes_exact=True)
+    check_state(name, pm.get_state(), sr, GPU, planes_exact=True)
     h, w = sr["costs"].shape
     for scale in (2, 1, 0):
         for it in range(3):
@@ -129,12 +147,14 @@ def test_live_all_sweeps_vs_reference(capi, oracle, name):
                 pm.half_sweep(red, it, scale)
                 ref.half_sweep(red, it, scale)
                 sr = ref.get_state()
-                check_state(name, pm.get_state(), sr, "gpu", upd=colour_mask(h, w, red))
+                check_state(name, pm.get_state(), sr, GPU, upd=colour_mask(h, w, red))
     pm.set_dev_state(sr)
     pm.finalize(); ref.finalize()
     a, b = pm.get_state(), ref.get_state()
     assert np.abs(a["planes"] - b["planes"]).max() < 1e-3 * (1 + np.abs(b["planes"]).max())   # GetDepthandNormal + median
     assert (a["planes"][..., 3] == b["planes"][..., 3]).mean() > 0.99
+    if arith == "exact":
+        np.testing.assert_array_equal(a["planes"], b["planes"])
     pm.destroy(); ref.destroy()
 
 
@@ -163,6 +183,9 @@ def test_live_full_run_config1(capi, oracle, pkg):
     print(f"agreement ours-ref (seed 1) {same_seed:.4f}; reference self-agreement across seeds {floor:.4f}")
     assert same_seed >= 0.98                               # >= 98% of valid pixels within 1% depth and 5 deg
     assert same_seed >= floor
+    for seed in (1, 2):                                    # the exact arithmetic (default): the reference's maps, bit for bit
+        np.testing.assert_array_equal(res["ours", seed][0], res["ref", seed][0])
+        np.testing.assert_array_equal(res["ours", seed][1], res["ref", seed][1])
     for seed in (1, 2):
         ao = synth.accuracy_at(res["ours", seed][0][..., 3], gt)
         ar = synth.accuracy_at(res["ref", seed][0][..., 3], gt)
@@ -194,7 +217,8 @@ def test_live_geom_and_prior_runs(capi, oracle, pkg):
     ag = synth.depth_normal_agreement(a[0][..., 3], a[0][..., :3], b[0][..., 3], b[0][..., :3], valid)
     ao, ar = synth.accuracy_at(a[0][..., 3], gt), synth.accuracy_at(b[0][..., 3], gt)
     print("prior run: agreement", ag, ao, ar)
-    assert ag > 0.93 and all(abs(x - y) <= 0.75 for x, y in zip(ao, ar))
+    np.testing.assert_array_equal(a[0], b[0])              # exact arithmetic (default): bit-identical whole prior run
+    np.testing.assert_array_equal(a[1], b[1])
     pm.destroy(); ref.destroy()
     # geom run from the previous result
     pm = capi.PatchMatch(0).set_problem(imgs, cams)
@@ -209,8 +233,8 @@ def test_live_geom_and_prior_runs(capi, oracle, pkg):
     ag = synth.depth_normal_agreement(a2[0][..., 3], a2[0][..., :3], b2[0][..., 3], b2[0][..., :3], valid)
     ao, ar = synth.accuracy_at(a2[0][..., 3], gt), synth.accuracy_at(b2[0][..., 3], gt)
     print("geom run: agreement", ag, ao, ar, "mean geom cost", a2[2].mean(), b2[2].mean())
-    assert ag > 0.93 and all(abs(x - y) <= 0.75 for x, y in zip(ao, ar))
-    assert abs(float(a2[2].mean()) - float(b2[2].mean())) < 0.02
+    for x, y in zip(a2, b2):                               # planes, costs and geometric costs of the whole geometric run
+        np.testing.assert_array_equal(x, y)
     pm.destroy(); ref.destroy()
 
 
@@ -463,6 +487,8 @@ def test_live_full_schedule_vs_reference(capi, oracle, pkg, planar, geom_planar)
         a, b = synth.accuracy_at(ours[i][0][..., 3], gt), synth.accuracy_at(state[i][0][..., 3], gt)
         dacc.append(max(abs(x - y) for x, y in zip(a, b)))
     print(f"schedule planar={planar} geom_planar={geom_planar}: agreement per view {[round(a, 4) for a in agree]}, max accuracy delta {max(dacc):.2f}")
-    # three chained stages (up to five Runs) of a chaotic algorithm: same-seed agreement decays from ~99 % per Run
+    # the kernels are bit-identical (tests/test_scene_parity_gpu.py shows whole scenes identical when both sides use the same
+    # priors); here each side runs its OWN host prior stage, whose planes differ in the last bits (closed form vs OpenCV's SVD):
+    # a chaotic algorithm then decorrelates to about what two seeds of the reference give. Accuracy is the bar that must hold.
     assert np.median(agree) > 0.94 and min(agree) > 0.90
     assert np.median(dacc) <= 0.5 and max(dacc) <= 1.5

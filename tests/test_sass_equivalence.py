@@ -73,7 +73,7 @@ def test_no_rsqrt_in_the_ncc_tail(sass):
 
 # md5 of the instruction text of the exact arithmetic's pipeline kernels (pm_exact::*) (sass_expr.pipeline_checksum) as they were when
 # tests/test_zz_fidelity_build_gpu.py measured them bit-identical to the reference on a B200 (nvcc 12.9.86, sm_100a).
-VERIFIED_ON_GPU = "cc02e6aa682809acad7bc283bed3c473"    # profiles/r02_fullsize_exact_v2.json, r02_fullsize_{prior,geom}_bisect_*.json
+VERIFIED_ON_GPU = "ff7e1e4ec2886b237501450ad57cb590"    # profiles/r02_fullsize_exact_v3.json, r02_gpu_tests_fid_v2.log
 
 
 def test_fidelity_kernels_are_the_ones_verified_on_the_gpu(sass):
