@@ -72,12 +72,14 @@ static void StoreColorPlyFileBinaryPointCloud(const std::string& path, const std
 }
 
 // RunFusion, PatchMatch.cpp:287-504 (host, single thread, pixel order and mask side effects as in the reference, the sky
-// gate of its BUILD_NCNN branch included when `Sky segment` is set). Colour: the grey image replicated to three channels.
+// gate of its BUILD_NCNN branch included when `Sky segment` is set). Colour: B, G, R of the colour image as the reference
+// averages them (cv::imread(IMREAD_COLOR), :322,399,443-445) when images/%08d.{ppm,jpg} decodes at the depth map's size; the
+// grey level in all three channels otherwise (a resized image: this OpenCV-free host has no 3-channel resize).
 size_t RunFusion(const ConfigParams& config, std::vector<Scene>& Scenes) {
     const size_t n = Scenes.size();
     std::vector<Camera> cams(n);
     std::vector<std::vector<float>> depths(n), normals(n);
-    std::vector<std::vector<unsigned char>> masks(n), sky(n);
+    std::vector<std::vector<unsigned char>> masks(n), sky(n), bgr(n);
     std::vector<int> W(n, 0), H(n, 0);
     const std::string image_folder = config.input_folder + "/images", cam_folder = config.input_folder + "/cams";
     for (size_t i = 0; i < n; ++i) {
@@ -104,6 +106,9 @@ size_t RunFusion(const ConfigParams& config, std::vector<Scene>& Scenes) {
             cams[i].K[0] *= sx; cams[i].K[2] *= sx; cams[i].K[4] *= sy; cams[i].K[5] *= sy;
         }
         cams[i].width = w; cams[i].height = h;
+        int cw = 0, ch = 0;
+        std::vector<unsigned char> col;
+        if (readColorFile(image_folder + "/" + id8(id), cw, ch, col) && cw == w && ch == h) bgr[i] = std::move(col);
     }
     std::map<int, int> id2index;
     for (size_t i = 0; i < n; ++i) if (Scenes[i].estimate) id2index[Scenes[i].refID] = (int)i;
@@ -126,6 +131,7 @@ size_t RunFusion(const ConfigParams& config, std::vector<Scene>& Scenes) {
                 float sumP[3] = {PX[0], PX[1], PX[2]}, sumN[3] = {rn[0], rn[1], rn[2]};
                 const float g = Scenes[i].image.px[idx];
                 float sumC[3] = {g, g, g};
+                if (!bgr[i].empty()) for (int k = 0; k < 3; ++k) sumC[k] = bgr[i][3 * idx + k];
                 int num_consistent = 0;
                 float dynamic_consistency = 0.f;
                 for (int j = 1; j < num_ngb; ++j) {
@@ -155,7 +161,7 @@ size_t RunFusion(const ConfigParams& config, std::vector<Scene>& Scenes) {
                         used_x[j] = sc; used_y[j] = sr;
                         for (int k = 0; k < 3; ++k) { sumP[k] += TX[k]; sumN[k] += sn[k]; }
                         const float sg = Scenes[s].image.px[sidx];
-                        sumC[0] += sg; sumC[1] += sg; sumC[2] += sg;
+                        for (int k = 0; k < 3; ++k) sumC[k] += bgr[s].empty() ? sg : (float)bgr[s][3 * sidx + k];
                         dynamic_consistency += std::exp(-(reproj + 200 * rel + angle * 10));
                         ++num_consistent;
                     }
@@ -227,6 +233,12 @@ size_t RunFusionGPU(const ConfigParams& config, std::vector<Scene>& Scenes) {
             gray_px = gray.data();
         }
         check(mpmvs_fusion_set_view(f, i, &cam, depth_px, normal_px, gray_px), "mpmvs_fusion_set_view");
+        {   // the colour image RunFusion averages (PatchMatch.cpp:322), when it decodes at the depth map's size
+            int cw = 0, ch = 0;
+            std::vector<unsigned char> col;
+            if (readColorFile(image_folder + "/" + id8(id), cw, ch, col) && cw == w && ch == h)
+                check(mpmvs_fusion_set_color(f, i, col.data()), "mpmvs_fusion_set_color");
+        }
         if (config.sky_seg) {
             const std::vector<unsigned char> sky = readSkyMask(folder, w, h);
             if (!sky.empty()) check(mpmvs_fusion_set_sky_mask(f, i, sky.data()), "mpmvs_fusion_set_sky_mask");
