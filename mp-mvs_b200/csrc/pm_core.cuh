@@ -64,6 +64,15 @@
 // (mpmvs_selftest_ex2_monotone, tests/test_zz_fidelity_build_gpu.py). A NaN prior fails at the first view, as it does at the end.
 #define PM_PRIOR_EARLY_OUT 1
 #endif
+#ifndef PM_PACKED
+// 1 (exact arithmetic, device): the tap loop of the NCC issues Blackwell's packed FP32 instructions (FFMA2 / FADD2 / FMUL2,
+// PTX fma/add/mul.rn.ftz.f32x2, new with sm_100): the numerators and coordinates of two neighbouring taps share one
+// instruction per operation, and so do the two products (w s, w r) and the two accumulations (sum w s s, sum w r s) of a tap.
+// Each lane of a packed instruction is the same IEEE operation with the same rounding and flush-to-zero as the scalar
+// instruction it replaces, so the results stay the reference's bits; what changes is the issue-slot count per tap (the exact
+// kernel is limited by instruction issue and the texture pipe about equally, profiles/r02_ncu_sweep_exact_v2.txt).
+#define PM_PACKED 1
+#endif
 #ifndef PM_VIEW_MAJOR
 // 1: the 8 x (N-1) candidate costs of a pixel are evaluated view by view (all candidates against source 0, then source 1,
 // ...) instead of candidate by candidate: eight consecutive NCCs of a block then sample the SAME source image, whose warped
@@ -185,6 +194,15 @@ PM_HD float pm_ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 // MUFU.RCP / MUFU.SQRT as such: `1.0f / sqrtf(x)` would be turned into one MUFU.RSQ, which the reference does not execute
 __device__ __forceinline__ float pm_rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float pm_sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// two floats in an aligned register pair and the packed FP32 instructions of sm_100 on them (FFMA2 / FADD2 / FMUL2). NOTE:
+// ptxas contracts a packed mul feeding a packed add into one FFMA2 even with .rn on both, so no pm_mul2 result may be the
+// addend-side input of a pm_add2 (none is: tests/test_sass_equivalence.py counts the instructions).
+struct pm_f2 { unsigned long long v; };
+__device__ __forceinline__ pm_f2 pm_pk(float lo, float hi) { pm_f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void pm_upk(pm_f2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ pm_f2 pm_fma2(pm_f2 a, pm_f2 b, pm_f2 c) { pm_f2 r; asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+__device__ __forceinline__ pm_f2 pm_mul2(pm_f2 a, pm_f2 b) { pm_f2 r; asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ pm_f2 pm_add2(pm_f2 a, pm_f2 b) { pm_f2 r; asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
 #else
 PM_HD float pm_rmul(float a, float b) { return a * b; }
 PM_HD float pm_radd(float a, float b) { return a + b; }
@@ -543,6 +561,54 @@ PM_HD float pm_ncc(const Ctx& c, const PmFrame& F, const PmRefStats& st, int v, 
     // Per tap: numerators FADD(H2, FFMA(H1, py, H0 px)), ...; MUFU.RCP(Z); coordinates FFMA(X, rcp, 0.5); FMUL r*w, FMUL s*w,
     // FADD sum(w s), FFMA(s, s*w, .), FFMA(s, r*w, .). Host: the oracle's divisions and unfused products, same order.
     float sum_src = 0.0f, sum_src_src = 0.0f, sum_ref_src = 0.0f;
+#if PM_PACKED && defined(__CUDA_ARCH__)
+    if (TAPS % 2 == 0) {
+        // The same operations, two per instruction (PM_PACKED above): taps (b, b + 1) of a row share the numerator and coordinate
+        // instructions; (w s, w r) of a tap are one FMUL2, (sum w s s, sum w r s) one FFMA2. The per-row and per-window sums are
+        // added in the reference's order (sequential FADDs per quantity), so nothing is reassociated.
+        const pm_f2 H1 = pm_pk(Hm[1], Hm[1]), H4 = pm_pk(Hm[4], Hm[4]), H7 = pm_pk(Hm[7], Hm[7]);
+        const pm_f2 H2 = pm_pk(Hm[2], Hm[2]), H5 = pm_pk(Hm[5], Hm[5]), H8 = pm_pk(Hm[8], Hm[8]);
+        const pm_f2 half2 = pm_pk(0.5f, 0.5f);
+#pragma unroll
+        for (int a = 0; a < TAPS; ++a) {
+            const int i = (2 * a - (TAPS - 1)) * HS;
+            const float px = (float)(x + i);
+            const float hx = pm_rmul(Hm[0], px), hy = pm_rmul(Hm[3], px), hz = pm_rmul(Hm[6], px);
+            const pm_f2 hx2 = pm_pk(hx, hx), hy2 = pm_pk(hy, hy), hz2 = pm_pk(hz, hz);
+            float row_src = 0.0f;
+            pm_f2 row2 = pm_pk(0.0f, 0.0f);          // (row_src_src, row_ref_src)
+#pragma unroll
+            for (int b = 0; b < TAPS; b += 2) {
+                const int j0 = (2 * b - (TAPS - 1)) * HS, j1 = (2 * b + 2 - (TAPS - 1)) * HS;
+                const pm_f2 py = pm_pk((float)(y + j0), (float)(y + j1));
+                const pm_f2 X = pm_add2(pm_fma2(H1, py, hx2), H2), Y = pm_add2(pm_fma2(H4, py, hy2), H5), Z = pm_add2(pm_fma2(H7, py, hz2), H8);
+                float z0, z1;
+                pm_upk(Z, z0, z1);
+                const pm_f2 rz = pm_pk(pm_rcp_approx(z0), pm_rcp_approx(z1));
+                float xs0, xs1, ys0, ys1;
+                pm_upk(pm_fma2(X, rz, half2), xs0, xs1);
+                pm_upk(pm_fma2(Y, rz, half2), ys0, ys1);
+                const float s0 = c.src(v, xs0, ys0), s1 = c.src(v, xs1, ys1);
+                const float r0 = c.ref(i, j0), r1 = c.ref(i, j1);
+                const float w0 = PM_WTAB ? c.wt(a * TAPS + b) : pm_tap_weight<SCALE, TAPS>(F, a, b, r0, st.r0);
+                const float w1 = PM_WTAB ? c.wt(a * TAPS + b + 1) : pm_tap_weight<SCALE, TAPS>(F, a, b + 1, r1, st.r0);
+                const pm_f2 p0 = pm_mul2(pm_pk(w0, w0), pm_pk(s0, r0)), p1 = pm_mul2(pm_pk(w1, w1), pm_pk(s1, r1));   // (w s, w r)
+                float sw0, rw0, sw1, rw1;
+                pm_upk(p0, sw0, rw0);
+                pm_upk(p1, sw1, rw1);
+                row_src = pm_radd(row_src, sw0);
+                row2 = pm_fma2(p0, pm_pk(s0, s0), row2);
+                row_src = pm_radd(row_src, sw1);
+                row2 = pm_fma2(p1, pm_pk(s1, s1), row2);
+            }
+            float row_src_src, row_ref_src;
+            pm_upk(row2, row_src_src, row_ref_src);
+            sum_src = pm_radd(sum_src, row_src);
+            sum_src_src = pm_radd(sum_src_src, row_src_src);
+            sum_ref_src = pm_radd(sum_ref_src, row_ref_src);
+        }
+    } else
+#endif
 #pragma unroll
     for (int a = 0; a < TAPS; ++a) {
         const int i = (2 * a - (TAPS - 1)) * HS;

@@ -15,6 +15,19 @@ import re
 import sys
 
 FP = {"FMUL": 2, "FADD": 2, "FFMA": 3}
+FP2 = {"FMUL2": "FMUL", "FADD2": "FADD", "FFMA2": "FFMA"}     # sm_100 packed FP32: two lanes, each the scalar operation
+
+
+def lane_operand(tok, lane, env):
+    """Operand of one lane of a packed instruction: `R4.F32x2.HI_LO` (or a bare `R4`) is the register pair (R4 = lane 0, R5 = lane 1),
+    `R4.F32` one register broadcast to both lanes."""
+    tok = tok.strip().replace(".reuse", "")
+    pair = ".F32x2" in tok or ".F32" not in tok
+    tok = tok.replace(".F32x2.HI_LO", "").replace(".F32", "")
+    m = re.fullmatch(r"(-?\|?)(U?R)(\d+)(\|?)", tok)
+    if m and pair and lane:
+        tok = f"{m.group(1)}{m.group(2)}{int(m.group(3)) + 1}{m.group(4)}"
+    return operand(tok, env)
 
 
 def function_body(path, name):
@@ -101,13 +114,19 @@ def run(body, stop_pc=None):
         args = [a.strip() for a in parts[1].split(",")] if len(parts) > 1 else []
         if op in FP and len(args) == FP[op] + 1:
             env[args[0]] = (op,) + tuple(operand(a, env) for a in args[1:])
+        elif op in FP2 and len(args) == FP[FP2[op]] + 1 and re.fullmatch(r"R\d+", args[0]):
+            base = int(args[0][1:])
+            lanes = [(FP2[op],) + tuple(lane_operand(a, lane, env) for a in args[1:]) for lane in (0, 1)]
+            env[f"R{base}"], env[f"R{base + 1}"] = lanes
         elif op == "MUFU" and len(args) == 2:
             kind = parts[0].split(".")[1].lower()
             env[args[0]] = (kind, operand(args[1], env))
         elif op == "I2FP" and len(args) == 2:
             env[args[0]] = ("i2f", operand(args[1], env))
-        elif op in ("MOV", "UMOV", "R2UR", "IMAD") and len(args) >= 2 and op != "IMAD":
+        elif op in ("MOV", "UMOV", "R2UR") and len(args) >= 2:
             env[args[0]] = operand(args[1], env)
+        elif parts[0].startswith("IMAD.MOV") and len(args) == 4 and args[1] == "RZ" and args[2] == "RZ":
+            env[args[0]] = operand(args[3], env)          # IMAD.MOV.U32 Rd, RZ, RZ, Rs: a register move on the integer pipe
         elif op in ("TEX", "TLD", "TLD4") and len(args) > 1:
             for a in args[:2]:                  # TEX RZ, Rdst, ... : the fetched texel is a fresh leaf
                 if re.fullmatch(r"R\d+", a):

@@ -14,6 +14,7 @@ OUT = os.path.join(ROOT, "mp-mvs_b200", "variants")
 # "default" = the in-tree defaults (PM_BH=4, PM_MIN_BLOCKS=3, PM_CA_SMEM=1, PM_UNIFORM_VIEWS=1, PM_EARLY_OUT=1, PM_WTAB=0)
 VARIANTS = {
     "default": [],
+    "nopacked": ["-DPM_PACKED=0"],                    # scalar FP32 instructions in the NCC tap loop (before FFMA2 / FADD2 / FMUL2)
     "noeo": ["-DPM_EARLY_OUT=0"],
     "nouv": ["-DPM_UNIFORM_VIEWS=0"],
     "mb2": ["-DPM_MIN_BLOCKS=2"],
