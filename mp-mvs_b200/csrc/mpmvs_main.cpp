@@ -170,9 +170,13 @@ size_t RunFusion(const ConfigParams& config, std::vector<Scene>& Scenes) {
                                                                  : (num_consistent >= 2);
                 if (!keep) continue;
                 PointList p;
+                // :454-460. consistent_normal is a cv::Vec3f: OpenCV's `operator/=(Vec&, float alpha)` (core/matx.hpp) multiplies by
+                // the float reciprocal `1.f / alpha`; the point and the colour are plain float divisions. Checked against the
+                // reference's own RunFusion compiled in place (tests/test_reference_program.py): the .ply is byte-identical.
+                const float ialpha = 1.f / (num_consistent + 1.0f);
                 for (int k = 0; k < 3; ++k) {
                     p.coord[k] = sumP[k] / (num_consistent + 1.0f);
-                    p.normal[k] = sumN[k] / (num_consistent + 1.0f);
+                    p.normal[k] = sumN[k] * ialpha;
                     p.color[k] = sumC[k] / (num_consistent + 1.0f);
                 }
                 cloud.push_back(p);

@@ -106,8 +106,10 @@ __global__ void __launch_bounds__(256) pm_fuse_kernel(const FusionView* views, i
     const bool ok = dynamic ? (num_consistent >= 1 && dyn > 0.3f * num_consistent) : (num_consistent >= 2);   // cpp:451,474
     if (!ok) return;
     FusedPoint p;
-    const float inv = 1.0f / (num_consistent + 1.0f);
-    for (int k = 0; k < 3; ++k) { p.coord[k] = sumP[k] * inv; p.normal[k] = sumN[k] * inv; p.color[k] = sumC[k] * inv; }
+    // cpp:454-460: the point and the colour are DIVIDED by (n + 1); the normal is a cv::Vec3f, whose `operator/=(float)` (OpenCV's
+    // core/matx.hpp) multiplies by the float reciprocal 1.f / alpha instead. IEEE operations whatever --use_fast_math says.
+    const float n1 = num_consistent + 1.0f, ialpha = __frcp_rn(n1);
+    for (int k = 0; k < 3; ++k) { p.coord[k] = __fdiv_rn(sumP[k], n1); p.normal[k] = __fmul_rn(sumN[k], ialpha); p.color[k] = __fdiv_rn(sumC[k], n1); }
     out[idx] = p;
     keep[idx] = 1;
     for (int j = 1; j < num_ngb; ++j)

@@ -98,8 +98,12 @@ def fuse(cams, depths, normals, grays, src_lists, dynamic=True, sky=None):
             numc[ok] += 1
             used[j] = (ok, src_r, src_c, s)
         keep = alive & ((numc >= 1) & (dyn > np.float32(0.3) * numc) if dynamic else (numc >= 2))
-        inv = (1.0 / (numc + 1.0)).astype(np.float32)
-        pts = np.concatenate([sumP * inv[..., None], sumN * inv[..., None], sumC * inv[..., None]], -1)
+        # cpp:454-460: point and colour are divided by (n + 1); the normal is a cv::Vec3f, whose operator/=(float) multiplies
+        # by the float reciprocal (OpenCV core/matx.hpp) -- pinned by the reference's own RunFusion, tests/test_reference_program.py
+        n1 = (numc + 1.0).astype(np.float32)
+        inv = (np.float32(1.0) / n1).astype(np.float32)
+        pts = np.concatenate([(sumP / n1[..., None]).astype(np.float32), (sumN * inv[..., None]).astype(np.float32),
+                              (sumC / n1[..., None]).astype(np.float32)], -1)
         out.append(pts[keep])
         for j, (ok, src_r, src_c, s) in used.items():
             m = ok & keep

@@ -1,0 +1,1 @@
+#include <opencv2/opencv.hpp>

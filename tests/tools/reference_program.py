@@ -1,0 +1,168 @@
+"""GPU tool (TEST INFRASTRUCTURE): the reference's WHOLE program -- main(), ProcessProblem, the planar-prior host stage,
+RunFusion, Run() and every kernel, compiled where they lie into oracle/_ref/libmpmvs_ref_host.so with OpenCV's numerics
+served by the real OpenCV (tests/ref_host.py) -- against the product's host program (mp-mvs_b200/mpmvs_main, reference
+order, exact arithmetic, float32 views) on the same dense folder with the same seeds. Compares the files both write
+(depths / normals / costs .dmb per image, MPMVS_model.ply) byte for byte, and, where the schedule has a planar prior, the
+prior the reference built (captured at its upload, PatchMatch.cpp:994-995) with mpmvs_build_prior on the same state.
+
+    python tests/tools/reference_program.py [--width 320 --height 240] [--schedules photo_geom,planar,geom_planar] [--golden out.npz]
+
+Prints one JSON line."""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+for p in (os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle"), ROOT):
+    sys.path.insert(0, p)
+
+from conftest import PKG  # noqa: E402
+import ref_host  # noqa: E402
+
+MAIN = os.path.join(ROOT, "mp-mvs_b200", "mpmvs_main")
+
+SCHEDULES = {   # config.yaml keys (utility.cpp:8-35); main.cpp:19-41 decides which ProcessProblem gets a planar prior
+    "photo_geom": {"Geometric consistency iterations": 2, "Planer prior": 0, "Geometric consistency planer prior": 0},
+    "planar": {"Geometric consistency iterations": 1, "Planer prior": 1, "Geometric consistency planer prior": 0},
+    "geom_planar": {"Geometric consistency iterations": 2, "Planer prior": 1, "Geometric consistency planer prior": 1},
+}
+
+
+def write_inputs(dense, width, height, seed):
+    """A rendered scene as a dense folder: JPEGs (what the reference decodes through cv::imread) plus the decoded .pgm / .ppm
+    sidecars the OpenCV-free product host reads, so both sides see the same pixels."""
+    import cv2
+
+    sc = PKG.synth.make_dtu_scene(width=width, height=height, grid=3, n_src=4, seed=seed, jpeg=True)
+    PKG.synth.write_dense_folder(sc, dense)
+    for i in range(sc.num_views):
+        bgr = cv2.imread(os.path.join(dense, "images", f"{i:08d}.jpg"), cv2.IMREAD_COLOR)
+        with open(os.path.join(dense, "images", f"{i:08d}.ppm"), "wb") as f:
+            f.write(b"P6\n%d %d\n255\n" % (bgr.shape[1], bgr.shape[0]))
+            f.write(np.ascontiguousarray(bgr[:, :, ::-1]).tobytes())
+    return sc
+
+
+def read_results(dense, n):
+    out = []
+    for i in range(n):
+        d = os.path.join(dense, "MPMVS", f"2333_{i:08d}")
+        out.append({k: open(os.path.join(d, k + ".dmb"), "rb").read() for k in ("depths", "normals", "costs")})
+    ply = open(os.path.join(dense, "MPMVS", "MPMVS_model.ply"), "rb").read()
+    return out, ply
+
+
+def ply_points(b):
+    h = b.index(b"end_header\n") + 11
+    return np.frombuffer(b[h:], np.dtype([("p", "<f4", 3), ("n", "<f4", 3), ("c", "u1", 3)]))
+
+
+def compare_prior(sc, cap, width, height):
+    """mpmvs_build_prior on the state the reference built its prior from, against the prior it uploaded."""
+    from mpmvs_b200 import capi
+
+    ref = int(cap["scene_index"])
+    ids, imgs, cams = sc.problem(ref, 4)
+    pm = capi.PatchMatch(0).set_problem(imgs, PKG.io_formats.pack_cameras(cams))
+    with_geom = cap["in_geom"] is not None
+    pm.set_geom_consistency_params(with_geom, with_geom)
+    pm.set_dev_state({"planes": cap["in_planes"].reshape(height, width, 4), "costs": cap["in_costs"].reshape(height, width), "views": None,
+                      "rng": None, "geom": cap["in_geom"].reshape(height, width) if with_geom else None})
+    verts = pm.pick_vertices(with_geom)                  # the three steps of mpmvs_build_prior (pm_capi.cu), which itself wants a Run() first
+    tris = capi.delaunay(verts, width, height)
+    pm.prior_from_triangles(verts, tris)
+    stats = {"n_vertices": len(verts), "n_triangles": len(tris)}
+    prior, mask = pm.get_prior()
+    pm.destroy()
+    if os.environ.get("REFPROG_DUMP"):
+        np.savez_compressed(os.environ["REFPROG_DUMP"] + f"_{ref}_{int(cap['stage'])}.npz", prior=prior, mask=mask, verts=verts, tris=tris)
+    rmask = cap["mask"].reshape(height, width)
+    rprior = cap["planes"].reshape(height, width, 4)
+    both = (mask > 0) & (rmask > 0)
+    d = np.abs(prior[both] - rprior[both])
+    # depth of the two prior planes at their pixel: what the kernels consume (PatchMatch.cu:552-562, 924-978)
+    return {"scene_index": int(ref), "stage": int(cap["stage"]), "geom_variant": bool(with_geom), "vertices": int(stats.get("n_vertices", -1)),
+            "triangles": int(stats.get("n_triangles", -1)), "reference_prior_pixels": float((rmask > 0).mean()), "our_prior_pixels": float((mask > 0).mean()),
+            "same_has_prior": float(((mask > 0) == (rmask > 0)).mean()), "planes_bit_identical": float((d == 0).all(-1).mean()) if both.any() else None,
+            "planes_within_1e-4": float((d < 1e-4).all(-1).mean()) if both.any() else None,
+            "planes_within_1e-3": float((d < 1e-3).all(-1).mean()) if both.any() else None, "max_abs_plane_diff": float(d.max()) if both.any() else None}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--width", type=int, default=320)
+    ap.add_argument("--height", type=int, default=240)
+    ap.add_argument("--schedules", default="photo_geom,planar,geom_planar")
+    ap.add_argument("--seed", type=int, default=7)
+    ap.add_argument("--golden", help="write the reference's captured priors (inputs and outputs) of the first image of every schedule here")
+    ap.add_argument("--keep", help="keep the working folders under this directory")
+    a = ap.parse_args()
+    assert ref_host.available(), "oracle/_ref/libmpmvs_ref_host.so is not built"
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "mp-mvs_b200", "csrc")])
+    work = a.keep or tempfile.mkdtemp(prefix="refprog_")
+    res = {"size": [a.width, a.height], "seed": a.seed, "schedules": {}}
+    golden = {}
+    for name in a.schedules.split(","):
+        cfg = dict(SCHEDULES[name], **{"Max source images num": 4})
+        sides = {}
+        for side in ("reference", "ours"):
+            proj = os.path.join(work, name, side)
+            shutil.rmtree(proj, ignore_errors=True)
+            dense = os.path.join(proj, "dense")
+            sc = write_inputs(dense, a.width, a.height, seed=2)
+            yaml = ref_host.write_project(proj, dense, **cfg)
+            t0 = time.time()
+            if side == "reference":
+                cap = os.path.join(proj, "priors.npz")
+                log = ref_host.run_main(proj, seed=a.seed, capture=cap)
+            else:
+                r = subprocess.run([MAIN, yaml, "--seed", str(a.seed), "--tex", "f32", "--arithmetic", "exact"], capture_output=True, text=True, timeout=3600)
+                assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+                log = r.stdout
+            sides[side] = {"wall_s": round(time.time() - t0, 2), "results": read_results(dense, sc.num_views), "log_tail": log[-300:]}
+        (ra, rply), (oa, oply) = sides["reference"]["results"], sides["ours"]["results"]
+        ident = {k: [bool(x[k] == y[k]) for x, y in zip(ra, oa)] for k in ("depths", "normals", "costs")}
+        entry = {"images": len(ra), "depth_maps_byte_identical": int(sum(ident["depths"])), "normal_maps_byte_identical": int(sum(ident["normals"])),
+                 "cost_maps_byte_identical": int(sum(ident["costs"])), "ply_byte_identical": bool(rply == oply),
+                 "ply_points": [int(len(ply_points(rply))), int(len(ply_points(oply)))],
+                 "wall_s": {k: v["wall_s"] for k, v in sides.items()}, "reference_opencv_calls": sides["reference"]["log_tail"].strip().splitlines()[-1]}
+        if not all(ident["depths"]):      # how close, where not identical
+            agree, accs = [], []
+            for i, (x, y) in enumerate(zip(ra, oa)):
+                dr = np.frombuffer(x["depths"][16:], np.float32).reshape(a.height, a.width)
+                do = np.frombuffer(y["depths"][16:], np.float32).reshape(a.height, a.width)
+                nr = np.frombuffer(x["normals"][16:], np.float32).reshape(a.height, a.width, 3)
+                no = np.frombuffer(y["normals"][16:], np.float32).reshape(a.height, a.width, 3)
+                agree.append(PKG.synth.depth_normal_agreement(do, no, dr, nr, sc.gt_depth[i] > 0))
+                accs.append([PKG.synth.accuracy_at(dr, sc.gt_depth[i])[0], PKG.synth.accuracy_at(do, sc.gt_depth[i])[0]])
+            entry["agreement_median_min"] = [float(np.median(agree)), float(np.min(agree))]
+            entry["accuracy_2cm_reference_ours"] = [float(np.mean([x[0] for x in accs])), float(np.mean([x[1] for x in accs]))]
+        z = np.load(os.path.join(work, name, "reference", "priors.npz"))
+        n_pri = int(z["n"])
+        entry["reference_priors_captured"] = n_pri
+        if n_pri:
+            caps = [{k: (z[f"p{j}_{k}"] if f"p{j}_{k}" in z.files else None) for k in ("scene_index", "stage", "planes", "mask", "in_planes", "in_costs", "in_geom")}
+                    for j in range(n_pri)]
+            entry["prior_stage"] = [compare_prior(sc, c, a.width, a.height) for c in caps[:3]]
+            if a.golden:
+                c = caps[0]
+                ids, imgs, cams = sc.problem(int(c["scene_index"]), 4)
+                golden.update({f"{name}/{k}": v for k, v in c.items() if v is not None})
+                golden[f"{name}/cams"] = PKG.io_formats.pack_cameras(cams)[:1]
+                golden[f"{name}/size"] = np.array([a.width, a.height], np.int32)
+        res["schedules"][name] = entry
+        print(name, json.dumps(entry), file=sys.stderr, flush=True)
+    if a.golden and golden:
+        import cv2
+
+        np.savez_compressed(a.golden, opencv_version=np.array(cv2.__version__), **golden)
+    if not a.keep:
+        shutil.rmtree(work, ignore_errors=True)
+    print(json.dumps(res))
