@@ -25,7 +25,7 @@
 
 #include "../../include/mpmvs_b200.h"
 #include "pm_core.cuh"
-#include "pm_delaunay.h"
+#include "pm_subdiv.h"
 #include "pm_kernels.h"
 #include "pm_views.h"
 
@@ -888,9 +888,8 @@ int mpmvs_delaunay(const int* xy, int n, int width, int height, int* tris_out, i
     if (!xy || n < 0 || width <= 0 || height <= 0 || !n_tris) return MPMVS_E_ARG;
     for (int i = 0; i < n; ++i)
         if (xy[2 * i] < 0 || xy[2 * i] >= width || xy[2 * i + 1] < 0 || xy[2 * i + 1] >= height) return MPMVS_E_ARG;
-    pmd::Delaunay d(xy, n, width, height);
     std::vector<int> t;
-    d.triangles(t);
+    if (!pmsd::triangulate(xy, n, width, height, t)) return MPMVS_E_ARG;
     *n_tris = (int)(t.size() / 3);
     if (tris_out) {
         if ((int)(t.size() / 3) > max_tris) return MPMVS_E_ARG;
@@ -994,10 +993,7 @@ int mpmvs_build_prior(mpmvs_problem* p, mpmvs_prior_stats* stats) {
     if (rc) return rc;
     const auto t1 = clk::now();
     std::vector<int> tris;
-    if (nv >= 3) {
-        pmd::Delaunay d(xy.data(), nv, p->W, p->H);
-        d.triangles(tris);
-    }
+    if (nv >= 3 && !pmsd::triangulate(xy.data(), nv, p->W, p->H, tris)) return MPMVS_E_ARG;   // triangle ORDER matters: pm_subdiv.h
     const auto t2 = clk::now();
     // vertices and triangles are copied with cudaMemcpyAsync from pageable vectors: the runtime stages them before returning
     rc = prior_from_trusted_triangles(p, xy.data(), nv, tris.data(), (int)(tris.size() / 3), nullptr);

@@ -1,6 +1,6 @@
 // pm_prior.cu -- device side of the planar-prior stage that ProcessProblem runs on the host between two Run()s
 // (/root/reference/src/PatchMatch.cpp:532-609, "cpp:NNN" below): vertex picking, triangle rasterisation to an id mask,
-// 3-point plane fit, depth-range check. Only the Delaunay triangulation itself stays on the host (pm_delaunay.h).
+// 3-point plane fit, depth-range check. Only the triangulation itself stays on the host (pm_subdiv.h).
 // Working on the state that the first Run() left in HBM avoids the reference's round trip: D2H of planes/costs, a
 // single-threaded host loop over every 5x5 cell, ~0.5 M cv::SVD::solveZ calls and a per-pixel H2D of float4 planes.
 #include <cuda_runtime.h>

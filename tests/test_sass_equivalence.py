@@ -71,9 +71,20 @@ def test_no_rsqrt_in_the_ncc_tail(sass):
     assert not any("MUFU.RSQ" in i for i in ref)
 
 
+def test_tap_loop_uses_blackwell_packed_fp32(sass):
+    """PM_PACKED (pm_core.cuh): two taps share one FFMA2 / FADD2 / FMUL2 per numerator, coordinate and moment -- every lane of a
+    packed instruction is the reference's own rounded operation (the coordinate trees above are read THROUGH the packed
+    instructions), so the results stay bit-identical with ~16 % fewer issue slots in the NCC."""
+    import sass_expr
+
+    body = [ins for _, ins in sass_expr.function_body(sass["lit"], SWEEP % 0)]
+    n = {k: sum(1 for i in body if i.split()[0].startswith(k)) for k in ("FFMA2", "FADD2", "FMUL2")}
+    assert n["FFMA2"] >= 100 and n["FADD2"] >= 36 and n["FMUL2"] >= 18, n
+
+
 # md5 of the instruction text of the exact arithmetic's pipeline kernels (pm_exact::*) (sass_expr.pipeline_checksum) as they were when
 # tests/test_zz_fidelity_build_gpu.py measured them bit-identical to the reference on a B200 (nvcc 12.9.86, sm_100a).
-VERIFIED_ON_GPU = "ff7e1e4ec2886b237501450ad57cb590"    # profiles/r02_fullsize_exact_v3.json, r02_gpu_tests_fid_v2.log
+VERIFIED_ON_GPU = "4f3b05a0ddfbac5c69cee218152f8927"    # profiles/r02_fullsize_exact_packed.json, r02_gpu_tests_fid_v3.log, r02_fullsize_geom_bisect_v2.json
 
 
 def test_fidelity_kernels_are_the_ones_verified_on_the_gpu(sass):

@@ -85,14 +85,13 @@ def compare_prior(sc, cap, width, height):
         np.savez_compressed(os.environ["REFPROG_DUMP"] + f"_{ref}_{int(cap['stage'])}.npz", prior=prior, mask=mask, verts=verts, tris=tris)
     rmask = cap["mask"].reshape(height, width)
     rprior = cap["planes"].reshape(height, width, 4)
-    both = (mask > 0) & (rmask > 0)
+    same = (mask == rmask)
+    both = same & (mask > 0)
     d = np.abs(prior[both] - rprior[both])
-    # depth of the two prior planes at their pixel: what the kernels consume (PatchMatch.cu:552-562, 924-978)
-    return {"scene_index": int(ref), "stage": int(cap["stage"]), "geom_variant": bool(with_geom), "vertices": int(stats.get("n_vertices", -1)),
-            "triangles": int(stats.get("n_triangles", -1)), "reference_prior_pixels": float((rmask > 0).mean()), "our_prior_pixels": float((mask > 0).mean()),
-            "same_has_prior": float(((mask > 0) == (rmask > 0)).mean()), "planes_bit_identical": float((d == 0).all(-1).mean()) if both.any() else None,
-            "planes_within_1e-4": float((d < 1e-4).all(-1).mean()) if both.any() else None,
-            "planes_within_1e-3": float((d < 1e-3).all(-1).mean()) if both.any() else None, "max_abs_plane_diff": float(d.max()) if both.any() else None}
+    return {"scene_index": int(ref), "stage": int(cap["stage"]), "geom_variant": bool(with_geom), "vertices": int(stats["n_vertices"]),
+            "triangles": int(stats["n_triangles"]), "reference_prior_pixels": float((rmask > 0).mean()), "our_prior_pixels": float((mask > 0).mean()),
+            "same_triangle_id": float(same.mean()), "planes_bit_identical_same_id": float((d == 0).all(-1).mean()) if both.any() else None,
+            "max_abs_plane_diff_same_id": float(d.max()) if both.any() else None, "mean_abs_plane_diff_same_id": float(d.mean()) if both.any() else None}
 
 
 if __name__ == "__main__":
@@ -154,6 +153,8 @@ if __name__ == "__main__":
             if a.golden:
                 c = caps[0]
                 ids, imgs, cams = sc.problem(int(c["scene_index"]), 4)
+                c = dict(c)
+                c["planes"] = np.where((c["mask"] > 0)[:, None], c["planes"].reshape(-1, 4), 0).astype(np.float32)   # undefined (new[]) where there is no prior
                 golden.update({f"{name}/{k}": v for k, v in c.items() if v is not None})
                 golden[f"{name}/cams"] = PKG.io_formats.pack_cameras(cams)[:1]
                 golden[f"{name}/size"] = np.array([a.width, a.height], np.int32)
