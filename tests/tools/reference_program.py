@@ -5,7 +5,7 @@ order, exact arithmetic, float32 views) on the same dense folder with the same s
 (depths / normals / costs .dmb per image, MPMVS_model.ply) byte for byte, and, where the schedule has a planar prior, the
 prior the reference built (captured at its upload, PatchMatch.cpp:994-995) with mpmvs_build_prior on the same state.
 
-    python tests/tools/reference_program.py [--width 320 --height 240] [--schedules photo_geom,planar,geom_planar] [--golden out.npz]
+    python tests/tools/reference_program.py [--scene small|dtu|eth3d] [--width W --height H] [--schedules photo_geom,planar,geom_planar] [--golden out.npz]
 
 Prints one JSON line."""
 import argparse
@@ -35,12 +35,22 @@ SCHEDULES = {   # config.yaml keys (utility.cpp:8-35); main.cpp:19-41 decides wh
 }
 
 
-def write_inputs(dense, width, height, seed):
+def render(kind, width, height, views):
+    """small: 9 views, 4 sources (the test's size); dtu / eth3d: the shapes of BASELINE.json configs[1] / [2] (49 views
+    1600x1200 and 11 views 3200x2130 by default, 10 sources)."""
+    workers = min(32, os.cpu_count() or 1)
+    if kind == "small":
+        return PKG.synth.make_dtu_scene(width=width, height=height, grid=3, n_src=4, seed=2, jpeg=True), 4
+    if kind == "dtu":
+        return PKG.synth.make_dtu_scene(width=width, height=height, workers=workers, jpeg=True), 10
+    return PKG.synth.make_eth3d_scene(width=width, height=height, n_views=views or 11, workers=workers, jpeg=True), 10
+
+
+def write_inputs(dense, sc):
     """A rendered scene as a dense folder: JPEGs (what the reference decodes through cv::imread) plus the decoded .pgm / .ppm
     sidecars the OpenCV-free product host reads, so both sides see the same pixels."""
     import cv2
 
-    sc = PKG.synth.make_dtu_scene(width=width, height=height, grid=3, n_src=4, seed=seed, jpeg=True)
     PKG.synth.write_dense_folder(sc, dense)
     for i in range(sc.num_views):
         bgr = cv2.imread(os.path.join(dense, "images", f"{i:08d}.jpg"), cv2.IMREAD_COLOR)
@@ -64,12 +74,12 @@ def ply_points(b):
     return np.frombuffer(b[h:], np.dtype([("p", "<f4", 3), ("n", "<f4", 3), ("c", "u1", 3)]))
 
 
-def compare_prior(sc, cap, width, height):
+def compare_prior(sc, cap, width, height, max_src=4):
     """mpmvs_build_prior on the state the reference built its prior from, against the prior it uploaded."""
     from mpmvs_b200 import capi
 
     ref = int(cap["scene_index"])
-    ids, imgs, cams = sc.problem(ref, 4)
+    ids, imgs, cams = sc.problem(ref, max_src)
     pm = capi.PatchMatch(0).set_problem(imgs, PKG.io_formats.pack_cameras(cams))
     with_geom = cap["in_geom"] is not None
     pm.set_geom_consistency_params(with_geom, with_geom)
@@ -96,33 +106,43 @@ def compare_prior(sc, cap, width, height):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--width", type=int, default=320)
-    ap.add_argument("--height", type=int, default=240)
+    ap.add_argument("--scene", default="small", choices=["small", "dtu", "eth3d"])
+    ap.add_argument("--views", type=int, default=0)
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--priors", type=int, default=3, help="how many of the captured priors to compare with the product's stage")
     ap.add_argument("--schedules", default="photo_geom,planar,geom_planar")
     ap.add_argument("--seed", type=int, default=7)
     ap.add_argument("--golden", help="write the reference's captured priors (inputs and outputs) of the first image of every schedule here")
     ap.add_argument("--keep", help="keep the working folders under this directory")
     a = ap.parse_args()
     assert ref_host.available(), "oracle/_ref/libmpmvs_ref_host.so is not built"
+    dw, dh = {"small": (320, 240), "dtu": (1600, 1200), "eth3d": (3200, 2130)}[a.scene]
+    a.width, a.height = a.width or dw, a.height or dh
+    t0 = time.time()
+    scene0, max_src = render(a.scene, a.width, a.height, a.views)
+    print(f"rendered {scene0.num_views} views {a.width}x{a.height} in {time.time() - t0:.1f} s", file=sys.stderr, flush=True)
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "mp-mvs_b200", "csrc")])
     work = a.keep or tempfile.mkdtemp(prefix="refprog_")
-    res = {"size": [a.width, a.height], "seed": a.seed, "schedules": {}}
+    res = {"scene": a.scene, "views": scene0.num_views, "size": [a.width, a.height], "max_src": max_src, "seed": a.seed, "schedules": {}}
     golden = {}
     for name in a.schedules.split(","):
-        cfg = dict(SCHEDULES[name], **{"Max source images num": 4})
+        cfg = dict(SCHEDULES[name], **{"Max source images num": max_src})
         sides = {}
         for side in ("reference", "ours"):
             proj = os.path.join(work, name, side)
             shutil.rmtree(proj, ignore_errors=True)
             dense = os.path.join(proj, "dense")
-            sc = write_inputs(dense, a.width, a.height, seed=2)
+            import copy
+
+            sc = write_inputs(dense, copy.deepcopy(scene0))
             yaml = ref_host.write_project(proj, dense, **cfg)
             t0 = time.time()
             if side == "reference":
                 cap = os.path.join(proj, "priors.npz")
-                log = ref_host.run_main(proj, seed=a.seed, capture=cap)
+                log = ref_host.run_main(proj, seed=a.seed, capture=cap, timeout=6000)
             else:
-                r = subprocess.run([MAIN, yaml, "--seed", str(a.seed), "--tex", "f32", "--arithmetic", "exact"], capture_output=True, text=True, timeout=3600)
+                r = subprocess.run([MAIN, yaml, "--seed", str(a.seed), "--tex", "f32", "--arithmetic", "exact"], capture_output=True, text=True, timeout=6000)
                 assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
                 log = r.stdout
             sides[side] = {"wall_s": round(time.time() - t0, 2), "results": read_results(dense, sc.num_views), "log_tail": log[-300:]}
@@ -149,10 +169,10 @@ if __name__ == "__main__":
         if n_pri:
             caps = [{k: (z[f"p{j}_{k}"] if f"p{j}_{k}" in z.files else None) for k in ("scene_index", "stage", "planes", "mask", "in_planes", "in_costs", "in_geom")}
                     for j in range(n_pri)]
-            entry["prior_stage"] = [compare_prior(sc, c, a.width, a.height) for c in caps[:3]]
+            entry["prior_stage"] = [compare_prior(sc, c, a.width, a.height, max_src) for c in caps[:a.priors]]
             if a.golden:
                 c = caps[0]
-                ids, imgs, cams = sc.problem(int(c["scene_index"]), 4)
+                ids, imgs, cams = sc.problem(int(c["scene_index"]), max_src)
                 c = dict(c)
                 c["planes"] = np.where((c["mask"] > 0)[:, None], c["planes"].reshape(-1, 4), 0).astype(np.float32)   # undefined (new[]) where there is no prior
                 golden.update({f"{name}/{k}": v for k, v in c.items() if v is not None})
