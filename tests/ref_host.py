@@ -50,6 +50,7 @@ class RefHost:
         self.lib.ref_host_get_prior.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         self.lib.ref_host_get_prior_input.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         self.counts = {"imread": 0, "resize": 0, "subdiv": 0, "solvez": 0}
+        self.solvez = os.environ.get("REF_HOST_SOLVEZ", "cv2")          # cv2 (the reference's own dependency) | numpy32 | numpy64
 
     # ---- the real OpenCV behind the stand-in headers
     def _imread(self, path, flags, rows, cols, channels, data):
@@ -90,8 +91,15 @@ class RefHost:
     def _solvez(self, A, rows, cols, z):
         self.counts["solvez"] += 1
         a = np.ctypeslib.as_array(A, shape=(rows, cols)).astype(np.float32)
-        # cv::SVD::solveZ = SVD(m, m.rows >= m.cols ? 0 : FULL_UV), last row of vt (modules/core/src/lapack.cpp)
-        _, _, vt = self.cv2.SVDecomp(a, flags=0 if rows >= cols else self.cv2.SVD_FULL_UV)
+        if self.solvez == "cv2":
+            # cv::SVD::solveZ = SVD(m, m.rows >= m.cols ? 0 : FULL_UV), last row of vt (modules/core/src/lapack.cpp)
+            _, _, vt = self.cv2.SVDecomp(a, flags=0 if rows >= cols else self.cv2.SVD_FULL_UV)
+        else:
+            # another, equally valid SVD (numpy's LAPACK in float32 or float64): what a reference linked against another OpenCV
+            # build would compute up to rounding noise -- used to measure how much of a whole-program difference is that noise
+            _, _, vt = np.linalg.svd(a.astype(np.float64 if self.solvez == "numpy64" else np.float32), full_matrices=True)
+            if vt[-1] @ self.cv2.SVDecomp(a, flags=self.cv2.SVD_FULL_UV)[2][-1] < 0:      # same sign convention as the default
+                vt = -vt
         out = np.ascontiguousarray(vt[-1], dtype=np.float32)
         ctypes.memmove(z, out.ctypes.data, 4 * cols)
         return 0
@@ -121,15 +129,17 @@ class RefHost:
         return out
 
 
-def _child(*args, timeout=3600):
-    r = subprocess.run([sys.executable, os.path.abspath(__file__), *map(str, args)], capture_output=True, text=True, timeout=timeout)
+def _child(*args, timeout=3600, env=None):
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), *map(str, args)], capture_output=True, text=True, timeout=timeout,
+                       env=dict(os.environ, **(env or {})))
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
     return r.stdout
 
 
-def run_main(project, seed=0, capture=None, timeout=3600):
-    """The reference's main() over <project>/config/config.yaml in a child process; `capture`: .npz for the priors it built."""
-    return _child("main", project, "--seed", seed, *(["--capture", capture] if capture else []), timeout=timeout)
+def run_main(project, seed=0, capture=None, timeout=3600, solvez="cv2"):
+    """The reference's main() over <project>/config/config.yaml in a child process; `capture`: .npz for the priors it built;
+    `solvez`: which SVD serves cv::SVD::solveZ (cv2 = the reference's own dependency)."""
+    return _child("main", project, "--seed", seed, *(["--capture", capture] if capture else []), timeout=timeout, env={"REF_HOST_SOLVEZ": solvez})
 
 
 def run_fusion(project, timeout=3600):

@@ -110,6 +110,8 @@ if __name__ == "__main__":
     ap.add_argument("--views", type=int, default=0)
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--svd-noise", action="store_true", help="also run the reference with another SVD behind cv::SVD::solveZ (numpy, float64) "
+                    "and report reference-against-reference agreement: how much of a difference is the plane fit's rounding noise")
     ap.add_argument("--priors", type=int, default=3, help="how many of the captured priors to compare with the product's stage")
     ap.add_argument("--schedules", default="photo_geom,planar,geom_planar")
     ap.add_argument("--seed", type=int, default=7)
@@ -129,7 +131,7 @@ if __name__ == "__main__":
     for name in a.schedules.split(","):
         cfg = dict(SCHEDULES[name], **{"Max source images num": max_src})
         sides = {}
-        for side in ("reference", "ours"):
+        for side in ("reference", "ours") + (("reference_other_svd",) if a.svd_noise and (cfg["Planer prior"] or cfg["Geometric consistency planer prior"]) else ()):
             proj = os.path.join(work, name, side)
             shutil.rmtree(proj, ignore_errors=True)
             dense = os.path.join(proj, "dense")
@@ -138,9 +140,9 @@ if __name__ == "__main__":
             sc = write_inputs(dense, copy.deepcopy(scene0))
             yaml = ref_host.write_project(proj, dense, **cfg)
             t0 = time.time()
-            if side == "reference":
+            if side.startswith("reference"):
                 cap = os.path.join(proj, "priors.npz")
-                log = ref_host.run_main(proj, seed=a.seed, capture=cap, timeout=6000)
+                log = ref_host.run_main(proj, seed=a.seed, capture=cap, timeout=6000, solvez="cv2" if side == "reference" else "numpy64")
             else:
                 r = subprocess.run([MAIN, yaml, "--seed", str(a.seed), "--tex", "f32", "--arithmetic", "exact"], capture_output=True, text=True, timeout=6000)
                 assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
@@ -152,17 +154,23 @@ if __name__ == "__main__":
                  "cost_maps_byte_identical": int(sum(ident["costs"])), "ply_byte_identical": bool(rply == oply),
                  "ply_points": [int(len(ply_points(rply))), int(len(ply_points(oply)))],
                  "wall_s": {k: v["wall_s"] for k, v in sides.items()}, "reference_opencv_calls": sides["reference"]["log_tail"].strip().splitlines()[-1]}
-        if not all(ident["depths"]):      # how close, where not identical
+        def closeness(xa, ya):
             agree, accs = [], []
-            for i, (x, y) in enumerate(zip(ra, oa)):
+            for i, (x, y) in enumerate(zip(xa, ya)):
                 dr = np.frombuffer(x["depths"][16:], np.float32).reshape(a.height, a.width)
                 do = np.frombuffer(y["depths"][16:], np.float32).reshape(a.height, a.width)
                 nr = np.frombuffer(x["normals"][16:], np.float32).reshape(a.height, a.width, 3)
                 no = np.frombuffer(y["normals"][16:], np.float32).reshape(a.height, a.width, 3)
                 agree.append(PKG.synth.depth_normal_agreement(do, no, dr, nr, sc.gt_depth[i] > 0))
                 accs.append([PKG.synth.accuracy_at(dr, sc.gt_depth[i])[0], PKG.synth.accuracy_at(do, sc.gt_depth[i])[0]])
-            entry["agreement_median_min"] = [float(np.median(agree)), float(np.min(agree))]
-            entry["accuracy_2cm_reference_ours"] = [float(np.mean([x[0] for x in accs])), float(np.mean([x[1] for x in accs]))]
+            return [float(np.median(agree)), float(np.min(agree))], [float(np.mean([x[0] for x in accs])), float(np.mean([x[1] for x in accs]))]
+
+        if not all(ident["depths"]):      # how close, where not identical
+            entry["agreement_median_min"], entry["accuracy_2cm_reference_ours"] = closeness(ra, oa)
+        if "reference_other_svd" in sides:   # the reference against itself with another SVD behind cv::SVD::solveZ
+            rb, _ = sides["reference_other_svd"]["results"]
+            entry["reference_vs_reference_other_svd"] = {"depth_maps_byte_identical": int(sum(x["depths"] == y["depths"] for x, y in zip(ra, rb)))}
+            entry["reference_vs_reference_other_svd"]["agreement_median_min"], entry["reference_vs_reference_other_svd"]["accuracy_2cm"] = closeness(ra, rb)
         z = np.load(os.path.join(work, name, "reference", "priors.npz"))
         n_pri = int(z["n"])
         entry["reference_priors_captured"] = n_pri
