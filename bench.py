@@ -440,7 +440,7 @@ def run_ours(args, rank, world, local_rank, prob, barrier, allmax, arithmetic=No
                      "executed_taps_per_step": int(taps_sweeps), "reference_equivalent_taps_per_step": int(ref_equiv_taps),
                      "gtaps_per_s": round(taps_sweeps / sweep_s / 1e9, 2),
                      "achieved_per_launch_bytes": int(taps_sweeps * BYTES_PER_TAP / max(1, n_sweeps)),
-                     "traffic_note": "DRAM bytes per sweep launch (ncu, profiles/r02_ncu_traffic.json): the source views once (300 MB as float32) + the per-pixel state a half-sweep reads and writes in 32-byte sectors that hold both checkerboard colours; < 1 % of the HBM peak -- the kernel is bound by the L1/TEX pipe and instruction issue (both ~70 % busy, profiles/r02_ncu_sweep_exact_v2.txt), not by DRAM",
+                     "traffic_note": "DRAM bytes per sweep launch (ncu, profiles/r02_ncu_traffic.json): the source views once (300 MB as float32) + the per-pixel state a half-sweep reads and writes in 32-byte sectors that hold both checkerboard colours; < 1 % of the HBM peak -- the kernel is bound by the L1 data stage, which texture and shared-memory wavefronts share: tex 72 % + lsu 23 % = 95 % busy (profiles/r02_ncu_sweep_exact_v2.txt, r02_l1_data_stage.md), not by DRAM",
                      "hbm_peak_gbs": peaks.get("hbm_gbs")},
         "clocks": clocks,
         "checksum_mean_cost": round(checksum, 6), "accuracy_2_5_10cm": [round(a, 3) for a in acc],

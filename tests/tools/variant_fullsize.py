@@ -2,7 +2,7 @@
 --check-ref, bit identity against the live reference of the WHOLE bench step: a same-seed photometric Run(), then -- with
 the same prior planes, those our planar-prior stage built -- a same-seed planar-prior Run(). No torch; prints one JSON line.
 
-    [MPMVS_ARITHMETIC=fast] [MPMVS_LIB_VARIANT=<tuning variant>] python tests/tools/variant_fullsize.py [--check-ref] [--tex u8]
+    [MPMVS_ARITHMETIC=fast] [MPMVS_LIB_VARIANT=<tuning variant>] python tests/tools/variant_fullsize.py [--check-ref] [--tex u8|f16|f32]
 """
 import json
 import os
@@ -22,10 +22,11 @@ from mpmvs_b200 import capi  # noqa: E402
 def main():
     t0 = time.time()
     prob = bench.load_problem("eth3d", 0, 1, lambda: None)
-    tex = "u8" if "--tex" in sys.argv and sys.argv[sys.argv.index("--tex") + 1] == "u8" else "f32"
+    tex = sys.argv[sys.argv.index("--tex") + 1] if "--tex" in sys.argv else "f32"
+    assert tex in ("u8", "f16", "f32")
     imgs = [i.astype(np.uint8) for i in prob["images"]] if tex == "u8" else prob["images"]
     out = {"variant": os.environ.get("MPMVS_LIB_VARIANT", "shipped"), "arithmetic": capi.default_arithmetic(), "tex": tex, "load_s": round(time.time() - t0, 1)}
-    pm = capi.PatchMatch(0).set_tex_format(capi.TEX_U8 if tex == "u8" else capi.TEX_F32).set_problem(imgs, prob["cams"])
+    pm = capi.PatchMatch(0).set_tex_format({"u8": capi.TEX_U8, "f16": capi.TEX_F16, "f32": capi.TEX_F32}[tex]).set_problem(imgs, prob["cams"])
     pm.set_geom_consistency_params(False, False)
     pm.run(1)                                           # warm-up
     out["photometric_run_ms"] = round(float(pm.run(2)), 2)
