@@ -166,17 +166,20 @@ def test_gpu_prior_stage_against_the_reference_programs_prior(name):
 @pytest.mark.skipif(not ref_host.available(), reason="oracle/_ref/libmpmvs_ref_host.so not built on this box")
 def test_whole_program_against_the_references_main():
     """The reference's main() and the product's mpmvs_main on the same dense folder, same seeds (9 views, 320x240):
-    * photometric + 2 geometric passes + fusion: every depths / normals / costs .dmb and MPMVS_model.ply BYTE-IDENTICAL;
+    * photometric + 2 geometric passes + fusion, and the same with a pair.txt that exercises GenerateSampleList's rules: every
+      depths / normals / costs .dmb and MPMVS_model.ply BYTE-IDENTICAL;
     * the two schedules with a planar prior: the product's prior has the reference's triangle id on every pixel and its planes
       within float32-SVD noise; the depth maps are then no longer bit-identical (that noise, amplified by the propagation)
       but agree on > 90 % of the pixels at 1 % depth / 5 degrees (measured 97.8 / 94.8 % median), with the same accuracy."""
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "reference_program.py")], capture_output=True, text=True, timeout=1800)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "reference_program.py"), "--schedules", "photo_geom,quirks,planar,geom_planar"],
+                       capture_output=True, text=True, timeout=1800)
     assert r.returncode == 0, r.stderr[-3000:]
     res = json.loads(r.stdout.strip().splitlines()[-1])["schedules"]
     print(json.dumps(res))
-    a = res["photo_geom"]
-    n = a["images"]
-    assert a["depth_maps_byte_identical"] == n and a["normal_maps_byte_identical"] == n and a["cost_maps_byte_identical"] == n and a["ply_byte_identical"], a
+    n = res["photo_geom"]["images"]
+    for name in ("photo_geom", "quirks"):      # quirks: a pair.txt with zero scores, too many sources, shuffled order; the >= 2 views fusion rule
+        a = res[name]
+        assert a["depth_maps_byte_identical"] == n and a["normal_maps_byte_identical"] == n and a["cost_maps_byte_identical"] == n and a["ply_byte_identical"], a
     for name in ("planar", "geom_planar"):
         b = res[name]
         assert b["reference_priors_captured"] == n

@@ -32,7 +32,28 @@ SCHEDULES = {   # config.yaml keys (utility.cpp:8-35); main.cpp:19-41 decides wh
     "photo_geom": {"Geometric consistency iterations": 2, "Planer prior": 0, "Geometric consistency planer prior": 0},
     "planar": {"Geometric consistency iterations": 1, "Planer prior": 1, "Geometric consistency planer prior": 0},
     "geom_planar": {"Geometric consistency iterations": 2, "Planer prior": 1, "Geometric consistency planer prior": 1},
+    # GenerateSampleList's rules (PatchMatch.cpp:67-109) on a pair.txt that exercises them: zero-score entries are dropped but
+    # still count towards `Max source images num` (the test is on the listed POSITION j), sources beyond it are ignored, the
+    # images are listed in another order than their ids, and the fusion rule without dynamic consistency (>= 2 views)
+    "quirks": {"Geometric consistency iterations": 1, "Planer prior": 0, "Geometric consistency planer prior": 0, "Max source images num": 3,
+               "Use dynamic_consistency to fuse": 0},
+    # images above `Max image size`: PatchMatchInit resizes them with cv::resize (PatchMatch.cpp:893-925) and RunFusion resizes the
+    # colour image (RescaleImageAndCamera, :264-285). OpenCV's resize is IPP / SIMD code; the product's own float resize agrees
+    # with it to 2e-3 grey levels, so this schedule is compared statistically
+    "resized": {"Geometric consistency iterations": 1, "Planer prior": 0, "Geometric consistency planer prior": 0, "Max image size": 200},
 }
+
+
+def quirky_pairs(path, sc):
+    order = list(range(sc.num_views))
+    with open(path, "w") as f:
+        f.write(f"{sc.num_views}\n")
+        for ref in order:
+            row = list(sc.pairs[ref])
+            row.insert(1, (row[-1][0], 0.0))            # a zero-score entry in second position
+            if ref % 2:
+                row = row[:1] + row[1:][::-1]            # and another order of the rest
+            f.write(f"{ref}\n{len(row)} " + " ".join(f"{i} {s:.4f}" for i, s in row) + "\n")
 
 
 def render(kind, width, height, views):
@@ -129,15 +150,17 @@ if __name__ == "__main__":
     res = {"scene": a.scene, "views": scene0.num_views, "size": [a.width, a.height], "max_src": max_src, "seed": a.seed, "schedules": {}}
     golden = {}
     for name in a.schedules.split(","):
-        cfg = dict(SCHEDULES[name], **{"Max source images num": max_src})
+        cfg = dict({"Max source images num": max_src}, **SCHEDULES[name])
         sides = {}
-        for side in ("reference", "ours") + (("reference_other_svd",) if a.svd_noise and (cfg["Planer prior"] or cfg["Geometric consistency planer prior"]) else ()):
+        for side in ("reference", "ours") + (("reference_other_svd",) if a.svd_noise and (cfg["Planer prior"] or cfg["Geometric consistency planer prior"]) else ()):   # noqa: E501
             proj = os.path.join(work, name, side)
             shutil.rmtree(proj, ignore_errors=True)
             dense = os.path.join(proj, "dense")
             import copy
 
             sc = write_inputs(dense, copy.deepcopy(scene0))
+            if name == "quirks":
+                quirky_pairs(os.path.join(dense, "pair.txt"), sc)
             yaml = ref_host.write_project(proj, dense, **cfg)
             t0 = time.time()
             if side.startswith("reference"):
@@ -157,12 +180,20 @@ if __name__ == "__main__":
         def closeness(xa, ya):
             agree, accs = [], []
             for i, (x, y) in enumerate(zip(xa, ya)):
-                dr = np.frombuffer(x["depths"][16:], np.float32).reshape(a.height, a.width)
-                do = np.frombuffer(y["depths"][16:], np.float32).reshape(a.height, a.width)
-                nr = np.frombuffer(x["normals"][16:], np.float32).reshape(a.height, a.width, 3)
-                no = np.frombuffer(y["normals"][16:], np.float32).reshape(a.height, a.width, 3)
-                agree.append(PKG.synth.depth_normal_agreement(do, no, dr, nr, sc.gt_depth[i] > 0))
-                accs.append([PKG.synth.accuracy_at(dr, sc.gt_depth[i])[0], PKG.synth.accuracy_at(do, sc.gt_depth[i])[0]])
+                hh, ww = (int(v) for v in np.frombuffer(x["depths"][4:12], np.int32))
+                if y["depths"][:16] != x["depths"][:16]:
+                    return [0.0, 0.0], [0.0, 0.0]
+                dr = np.frombuffer(x["depths"][16:], np.float32).reshape(hh, ww)
+                do = np.frombuffer(y["depths"][16:], np.float32).reshape(hh, ww)
+                nr = np.frombuffer(x["normals"][16:], np.float32).reshape(hh, ww, 3)
+                no = np.frombuffer(y["normals"][16:], np.float32).reshape(hh, ww, 3)
+                gt = sc.gt_depth[i]
+                if (hh, ww) != gt.shape:      # ground truth at the resized pixel centres (nearest full-size pixel)
+                    ys = np.clip(np.rint((np.arange(hh) + 0.5) * gt.shape[0] / hh - 0.5).astype(int), 0, gt.shape[0] - 1)
+                    xs = np.clip(np.rint((np.arange(ww) + 0.5) * gt.shape[1] / ww - 0.5).astype(int), 0, gt.shape[1] - 1)
+                    gt = gt[ys][:, xs]
+                agree.append(PKG.synth.depth_normal_agreement(do, no, dr, nr, gt > 0))
+                accs.append([PKG.synth.accuracy_at(dr, gt)[0], PKG.synth.accuracy_at(do, gt)[0]])
             return [float(np.median(agree)), float(np.min(agree))], [float(np.mean([x[0] for x in accs])), float(np.mean([x[1] for x in accs]))]
 
         if not all(ident["depths"]):      # how close, where not identical
