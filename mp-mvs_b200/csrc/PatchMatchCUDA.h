@@ -77,6 +77,7 @@ bool writeDmb(const std::string& path, int h, int w, int nb, const float* data);
 bool readGrayImage(const std::string& image_folder, int id, GrayImage& out);    // %08d.pgm (decoded sidecar) or %08d.jpg (nvJPEG)
 bool readGrayFile(const std::string& path_without_ext, GrayImage& out);        // <path>.pgm or <path>.jpg (nvJPEG luma)
 bool readColorFile(const std::string& path_without_ext, int& w, int& h, std::vector<unsigned char>& bgr);   // .ppm or .jpg, B G R interleaved
+std::vector<unsigned char> resizeLinearBGR(const std::vector<unsigned char>& src, int width, int height, int new_cols, int new_rows);   // cv::resize, CV_8UC3, INTER_LINEAR
 bool writePgm(const std::string& path, int w, int h, const unsigned char* px);
 GrayImage resizeLinear(const GrayImage& src, int new_cols, int new_rows);       // cv::resize(..., INTER_LINEAR) on float
 // Background .dmb writers: ProcessProblem hands its three result maps over and returns; Flush() waits for the files

@@ -412,6 +412,51 @@ GrayImage resizeLinear(const GrayImage& src, int new_cols, int new_rows) {
     return dst;
 }
 
+// cv::resize(src, dst, Size(new_cols, new_rows), 0, 0, INTER_LINEAR) for CV_8UC3 (RescaleImageAndCamera, PatchMatch.cpp:277):
+// OpenCV's 8-bit path is fixed point -- the two weights of a sample rounded to 11 bits, the horizontal pass kept as a 32-bit
+// integer, the vertical pass ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16), rounded by (+2) >> 2 -- with the same pixel-centre
+// mapping and border rule as the float path above. Byte-identical to cv2.resize of an OpenCV build without IPP
+// (tests/test_cpp_host.py); Intel IPP, where OpenCV is built with it, answers up to 1 grey level differently.
+std::vector<unsigned char> resizeLinearBGR(const std::vector<unsigned char>& src, int width, int height, int new_cols, int new_rows) {
+    std::vector<unsigned char> dst((size_t)new_cols * new_rows * 3);
+    const double sx = (double)width / new_cols, sy = (double)height / new_rows;
+    std::vector<int> x0(new_cols), a0(new_cols), a1(new_cols);
+    for (int dx = 0; dx < new_cols; ++dx) {
+        float fx = (float)((dx + 0.5) * sx - 0.5);
+        int ix = (int)std::floor(fx);
+        fx -= ix;
+        if (ix < 0) { ix = 0; fx = 0.f; }
+        if (ix >= width - 1) { ix = width - 1; fx = 0.f; }
+        x0[dx] = ix;
+        a0[dx] = (int)std::lrint((1.f - fx) * 2048.f);
+        a1[dx] = (int)std::lrint(fx * 2048.f);
+    }
+    std::vector<int> row0((size_t)new_cols * 3), row1((size_t)new_cols * 3);
+    auto hpass = [&](int iy, std::vector<int>& out) {
+        const unsigned char* r = &src[(size_t)iy * width * 3];
+        for (int dx = 0; dx < new_cols; ++dx) {
+            const int i0 = x0[dx], i1 = std::min(i0 + 1, width - 1);
+            for (int k = 0; k < 3; ++k) out[(size_t)dx * 3 + k] = r[i0 * 3 + k] * a0[dx] + r[i1 * 3 + k] * a1[dx];
+        }
+    };
+    for (int dy = 0; dy < new_rows; ++dy) {
+        float fy = (float)((dy + 0.5) * sy - 0.5);
+        int iy = (int)std::floor(fy);
+        fy -= iy;
+        if (iy < 0) { iy = 0; fy = 0.f; }
+        if (iy >= height - 1) { iy = height - 1; fy = 0.f; }
+        const int b0 = (int)std::lrint((1.f - fy) * 2048.f), b1 = (int)std::lrint(fy * 2048.f);
+        hpass(iy, row0);
+        hpass(std::min(iy + 1, height - 1), row1);
+        unsigned char* d = &dst[(size_t)dy * new_cols * 3];
+        for (int k = 0; k < new_cols * 3; ++k) {
+            const int v = (((b0 * (row0[k] >> 4)) >> 16) + ((b1 * (row1[k] >> 4)) >> 16) + 2) >> 2;
+            d[k] = (unsigned char)std::min(255, std::max(0, v));
+        }
+    }
+    return dst;
+}
+
 // ---------------------------------------------------------------------------------------------- class members
 void PatchMatchCUDA::PatchMatchInit(std::vector<Scene>& Scenes, int ID) {
     images_.clear(); depths_.clear(); cameras_.clear();

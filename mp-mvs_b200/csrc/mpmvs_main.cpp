@@ -73,8 +73,9 @@ static void StoreColorPlyFileBinaryPointCloud(const std::string& path, const std
 
 // RunFusion, PatchMatch.cpp:287-504 (host, single thread, pixel order and mask side effects as in the reference, the sky
 // gate of its BUILD_NCNN branch included when `Sky segment` is set). Colour: B, G, R of the colour image as the reference
-// averages them (cv::imread(IMREAD_COLOR), :322,399,443-445) when images/%08d.{ppm,jpg} decodes at the depth map's size; the
-// grey level in all three channels otherwise (a resized image: this OpenCV-free host has no 3-channel resize).
+// averages them (cv::imread(IMREAD_COLOR), :322,399,443-445) from images/%08d.{ppm,jpg}, resized to the depth map's size like
+// RescaleImageAndCamera does (resizeLinearBGR = cv::resize's 8-bit fixed-point path); the grey level in all three channels
+// when there is no colour file.
 size_t RunFusion(const ConfigParams& config, std::vector<Scene>& Scenes) {
     const size_t n = Scenes.size();
     std::vector<Camera> cams(n);
@@ -108,7 +109,8 @@ size_t RunFusion(const ConfigParams& config, std::vector<Scene>& Scenes) {
         cams[i].width = w; cams[i].height = h;
         int cw = 0, ch = 0;
         std::vector<unsigned char> col;
-        if (readColorFile(image_folder + "/" + id8(id), cw, ch, col) && cw == w && ch == h) bgr[i] = std::move(col);
+        if (readColorFile(image_folder + "/" + id8(id), cw, ch, col))              // RescaleImageAndCamera, :264-285: the colour image at the depth map's size
+            bgr[i] = (cw == w && ch == h) ? std::move(col) : resizeLinearBGR(col, cw, ch, w, h);
     }
     std::map<int, int> id2index;
     for (size_t i = 0; i < n; ++i) if (Scenes[i].estimate) id2index[Scenes[i].refID] = (int)i;
@@ -240,8 +242,10 @@ size_t RunFusionGPU(const ConfigParams& config, std::vector<Scene>& Scenes) {
         {   // the colour image RunFusion averages (PatchMatch.cpp:322), when it decodes at the depth map's size
             int cw = 0, ch = 0;
             std::vector<unsigned char> col;
-            if (readColorFile(image_folder + "/" + id8(id), cw, ch, col) && cw == w && ch == h)
+            if (readColorFile(image_folder + "/" + id8(id), cw, ch, col)) {
+                if (cw != w || ch != h) col = resizeLinearBGR(col, cw, ch, w, h);
                 check(mpmvs_fusion_set_color(f, i, col.data()), "mpmvs_fusion_set_color");
+            }
         }
         if (config.sky_seg) {
             const std::vector<unsigned char> sky = readSkyMask(folder, w, h);

@@ -22,7 +22,16 @@ from conftest import PKG  # noqa: E402
 import ref_host  # noqa: E402
 
 
-def build_folder(dense, n_noise=0.03):
+def half_size(a, h, w):
+    """Samples a full-size map at the pixel centres of the (h, w) image (nearest full-size pixel)."""
+    ys = np.clip(np.rint((np.arange(h) + 0.5) * a.shape[0] / h - 0.5).astype(int), 0, a.shape[0] - 1)
+    xs = np.clip(np.rint((np.arange(w) + 0.5) * a.shape[1] / w - 0.5).astype(int), 0, a.shape[1] - 1)
+    return np.ascontiguousarray(a[ys][:, xs])
+
+
+def build_folder(dense, n_noise=0.03, map_size=None):
+    """map_size (h, w): depth and normal maps smaller than the images, as `Max image size` produces them -- RunFusion then
+    resizes the colour image and scales K (RescaleImageAndCamera, PatchMatch.cpp:264-285)."""
     import cv2
 
     sc = PKG.synth.make_dtu_scene(width=96, height=72, grid=2, n_src=3, seed=4, jpeg=True)
@@ -37,9 +46,12 @@ def build_folder(dense, n_noise=0.03):
         d = os.path.join(dense, "MPMVS", f"2333_{i:08d}")
         os.makedirs(d, exist_ok=True)
         gt = sc.gt_depth[i].astype(np.float32)
+        gn = sc.gt_normal[i].astype(np.float32)
+        if map_size:
+            gt, gn = half_size(gt, *map_size), half_size(gn, *map_size)
         dep = (gt * (1 + 0.002 * rng.standard_normal(gt.shape))).astype(np.float32)
         dep[rng.random(gt.shape) < 0.05] = 0
-        nrm = sc.gt_normal[i].astype(np.float32) + n_noise * rng.standard_normal(sc.gt_normal[i].shape).astype(np.float32)
+        nrm = gn + n_noise * rng.standard_normal(gn.shape).astype(np.float32)
         nrm = (nrm / np.linalg.norm(nrm, axis=-1, keepdims=True)).astype(np.float32)
         PKG.io_formats.write_dmb(os.path.join(d, "depths.dmb"), dep)
         PKG.io_formats.write_dmb(os.path.join(d, "normals.dmb"), nrm)
@@ -69,6 +81,16 @@ if __name__ == "__main__":
         ref_host.run_fusion(work)
         out[f"ply_dyn{dyn}"] = ply_vertices(os.path.join(dense, "MPMVS", "MPMVS_model.ply"))
         print("dynamic consistency", dyn, ":", len(out[f"ply_dyn{dyn}"]) // 27, "points")
+    # the same images with 64 x 48 maps: the colour images are resized by cv::resize (OpenCV's own 8-bit path: IPP off)
+    dense2 = os.path.join(work, "dense_small_maps")
+    _, files2 = build_folder(dense2, map_size=(48, 64))
+    for k, v in files2.items():
+        if k.startswith(("depth", "normal")):
+            out["small_" + k] = v
+    ref_host.write_project(work, dense2, **{"Use dynamic_consistency to fuse": 1, "Max source images num": 3})
+    ref_host.run_fusion(work, ipp=False)
+    out["ply_small_maps_dyn1"] = ply_vertices(os.path.join(dense2, "MPMVS", "MPMVS_model.ply"))
+    print("64 x 48 maps of 96 x 72 images:", len(out["ply_small_maps_dyn1"]) // 27, "points")
     np.savez_compressed(os.path.join(HERE, "ref_fusion.npz"), **out)
     shutil.rmtree(work, ignore_errors=True)
     print("ref_fusion.npz", os.path.getsize(os.path.join(HERE, "ref_fusion.npz")) // 1024, "KB")

@@ -51,6 +51,8 @@ class RefHost:
         self.lib.ref_host_get_prior_input.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         self.counts = {"imread": 0, "resize": 0, "subdiv": 0, "solvez": 0}
         self.solvez = os.environ.get("REF_HOST_SOLVEZ", "cv2")          # cv2 (the reference's own dependency) | numpy32 | numpy64
+        if os.environ.get("REF_HOST_IPP", "1") == "0":                  # OpenCV's own resize instead of Intel IPP's (a build without IPP)
+            cv2.ipp.setUseIPP(False)
 
     # ---- the real OpenCV behind the stand-in headers
     def _imread(self, path, flags, rows, cols, channels, data):
@@ -136,14 +138,16 @@ def _child(*args, timeout=3600, env=None):
     return r.stdout
 
 
-def run_main(project, seed=0, capture=None, timeout=3600, solvez="cv2"):
+def run_main(project, seed=0, capture=None, timeout=3600, solvez="cv2", ipp=True):
     """The reference's main() over <project>/config/config.yaml in a child process; `capture`: .npz for the priors it built;
-    `solvez`: which SVD serves cv::SVD::solveZ (cv2 = the reference's own dependency)."""
-    return _child("main", project, "--seed", seed, *(["--capture", capture] if capture else []), timeout=timeout, env={"REF_HOST_SOLVEZ": solvez})
+    `solvez`: which SVD serves cv::SVD::solveZ (cv2 = the reference's own dependency); `ipp`: False = OpenCV's own cv::resize
+    (what a build without Intel IPP runs; IPP's resize answers up to 3e-3 grey levels / 1 level of 255 differently)."""
+    return _child("main", project, "--seed", seed, *(["--capture", capture] if capture else []), timeout=timeout,
+                  env={"REF_HOST_SOLVEZ": solvez, "REF_HOST_IPP": "1" if ipp else "0"})
 
 
-def run_fusion(project, timeout=3600):
-    return _child("fusion", project, timeout=timeout)
+def run_fusion(project, timeout=3600, ipp=True):
+    return _child("fusion", project, timeout=timeout, env={"REF_HOST_IPP": "1" if ipp else "0"})
 
 
 def write_project(project, dense, **cfg):

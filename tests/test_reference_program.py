@@ -34,13 +34,13 @@ def ply_vertices(path):
     return np.frombuffer(b[b.index(b"end_header\n") + 11:], np.uint8)
 
 
-def golden_fusion_folder(tmp_path):
+def golden_fusion_folder(tmp_path, maps=""):
     """Rebuilds the dense folder the golden file was made from; the product host reads decoded sidecars (it has no JPEG
-    decoder of OpenCV's): the pixels cv2.imread returns for the stored JPEG bytes."""
+    decoder of OpenCV's): the pixels cv2.imread returns for the stored JPEG bytes. maps="small_": the 64 x 48 maps."""
     import cv2
 
     z = np.load(os.path.join(GOLD, "ref_fusion.npz"))
-    dense = str(tmp_path / "dense")
+    dense = str(tmp_path / ("dense" + maps))
     for sub in ("images", "cams", "MPMVS"):
         os.makedirs(os.path.join(dense, sub), exist_ok=True)
     open(os.path.join(dense, "pair.txt"), "wb").write(z["pair.txt"].tobytes())
@@ -55,8 +55,8 @@ def golden_fusion_folder(tmp_path):
             f.write(np.ascontiguousarray(bgr[:, :, ::-1]).tobytes())
         d = os.path.join(dense, "MPMVS", f"2333_{i:08d}")
         os.makedirs(d, exist_ok=True)
-        io_formats.write_dmb(os.path.join(d, "depths.dmb"), z[f"depth{i}"])
-        io_formats.write_dmb(os.path.join(d, "normals.dmb"), z[f"normal{i}"])
+        io_formats.write_dmb(os.path.join(d, "depths.dmb"), z[f"{maps}depth{i}"])
+        io_formats.write_dmb(os.path.join(d, "normals.dmb"), z[f"{maps}normal{i}"])
     return z, dense
 
 
@@ -76,6 +76,20 @@ def test_host_fusion_reproduces_the_references_ply(tmp_path, dyn):
     np.testing.assert_array_equal(got, want)
 
 
+def test_host_fusion_with_smaller_maps_reproduces_the_references_ply(tmp_path):
+    """Depth maps smaller than the images (what `Max image size` produces): RunFusion resizes the colour image and scales K
+    (RescaleImageAndCamera, PatchMatch.cpp:264-285). The host's resizeLinearBGR is cv::resize's 8-bit fixed-point path, so the
+    .ply is byte-identical to the reference's with OpenCV's own resize (Intel IPP, where OpenCV has it, differs by a grey level)."""
+    build_main()
+    z, dense = golden_fusion_folder(tmp_path, "small_")
+    yaml = ref_host.write_project(str(tmp_path), dense, **{"Use dynamic_consistency to fuse": 1, "Max source images num": 3})
+    r = subprocess.run([MAIN, yaml, "--fusion-only"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    got = ply_vertices(os.path.join(dense, "MPMVS", "MPMVS_model.ply"))
+    assert len(z["ply_small_maps_dyn1"]) // 27 > 500
+    np.testing.assert_array_equal(got, z["ply_small_maps_dyn1"])
+
+
 @pytest.mark.skipif(not ref_host.available(), reason="oracle/_ref/libmpmvs_ref_host.so not built here")
 def test_golden_fusion_is_what_the_reference_writes_today(tmp_path):
     """The frozen file against the live library: the reference's RunFusion on the rebuilt folder."""
@@ -84,6 +98,10 @@ def test_golden_fusion_is_what_the_reference_writes_today(tmp_path):
         ref_host.write_project(str(tmp_path), dense, **{"Use dynamic_consistency to fuse": dyn, "Max source images num": 3})
         ref_host.run_fusion(str(tmp_path))
         np.testing.assert_array_equal(ply_vertices(os.path.join(dense, "MPMVS", "MPMVS_model.ply")), z[f"ply_dyn{dyn}"])
+    z, dense = golden_fusion_folder(tmp_path, "small_")
+    ref_host.write_project(str(tmp_path), dense, **{"Use dynamic_consistency to fuse": 1, "Max source images num": 3})
+    ref_host.run_fusion(str(tmp_path), ipp=False)
+    np.testing.assert_array_equal(ply_vertices(os.path.join(dense, "MPMVS", "MPMVS_model.ply")), z["ply_small_maps_dyn1"])
 
 
 def prior_cases():
@@ -166,18 +184,20 @@ def test_gpu_prior_stage_against_the_reference_programs_prior(name):
 @pytest.mark.skipif(not ref_host.available(), reason="oracle/_ref/libmpmvs_ref_host.so not built on this box")
 def test_whole_program_against_the_references_main():
     """The reference's main() and the product's mpmvs_main on the same dense folder, same seeds (9 views, 320x240):
-    * photometric + 2 geometric passes + fusion, and the same with a pair.txt that exercises GenerateSampleList's rules: every
-      depths / normals / costs .dmb and MPMVS_model.ply BYTE-IDENTICAL;
+    * photometric + 2 geometric passes + fusion; a pair.txt that exercises GenerateSampleList's rules; images above `Max image
+      size`: every depths / normals / costs .dmb and MPMVS_model.ply BYTE-IDENTICAL;
     * the two schedules with a planar prior: the product's prior has the reference's triangle id on every pixel and its planes
       within float32-SVD noise; the depth maps are then no longer bit-identical (that noise, amplified by the propagation)
       but agree on > 90 % of the pixels at 1 % depth / 5 degrees (measured 97.8 / 94.8 % median), with the same accuracy."""
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "reference_program.py"), "--schedules", "photo_geom,quirks,planar,geom_planar"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "reference_program.py"), "--schedules", "photo_geom,quirks,resized,planar,geom_planar"],
                        capture_output=True, text=True, timeout=1800)
     assert r.returncode == 0, r.stderr[-3000:]
     res = json.loads(r.stdout.strip().splitlines()[-1])["schedules"]
     print(json.dumps(res))
     n = res["photo_geom"]["images"]
-    for name in ("photo_geom", "quirks"):      # quirks: a pair.txt with zero scores, too many sources, shuffled order; the >= 2 views fusion rule
+    # quirks: a pair.txt with zero scores, too many sources, shuffled order, the >= 2 views fusion rule; resized: `Max image size`
+    # below the image size (PatchMatchInit's cv::resize + K scaling, RunFusion's colour resize; OpenCV's own resize, IPP off)
+    for name in ("photo_geom", "quirks", "resized"):
         a = res[name]
         assert a["depth_maps_byte_identical"] == n and a["normal_maps_byte_identical"] == n and a["cost_maps_byte_identical"] == n and a["ply_byte_identical"], a
     for name in ("planar", "geom_planar"):
