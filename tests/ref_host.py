@@ -41,7 +41,8 @@ class RefHost:
         self.cv2 = cv2
         self.lib = ctypes.CDLL(LIB)
         self.keep = {}
-        self.cb = (IMREAD(self._imread), RESIZE(self._resize), SUBDIV(self._subdiv), SOLVEZ(self._solvez))
+        self.cb = (IMREAD(self._guard(self._imread)), RESIZE(self._guard(self._resize)), SUBDIV(self._guard(self._subdiv)),
+                   SOLVEZ(self._guard(self._solvez)))
         self.lib.ref_host_set_callbacks(*self.cb)
         self.lib.ref_host_set_seed_plan.argtypes = [ctypes.c_ulonglong] * 4
         self.lib.ref_host_main.argtypes = [ctypes.c_char_p]
@@ -54,7 +55,18 @@ class RefHost:
         if os.environ.get("REF_HOST_IPP", "1") == "0":                  # OpenCV's own resize instead of Intel IPP's (a build without IPP)
             cv2.ipp.setUseIPP(False)
 
-    # ---- the real OpenCV behind the stand-in headers
+    # ---- the real OpenCV behind the stand-in headers (a Python exception inside a ctypes callback would be swallowed and
+    # leave the outputs unset: every callback reports failure through its return value instead, and the stand-in aborts)
+    @staticmethod
+    def _guard(fn):
+        def wrapped(*a):
+            try:
+                return fn(*a)
+            except Exception as e:      # noqa: BLE001
+                print("ref_host callback failed:", repr(e), file=sys.stderr, flush=True)
+                return 1
+        return wrapped
+
     def _imread(self, path, flags, rows, cols, channels, data):
         self.counts["imread"] += 1
         img = self.cv2.imread(path.decode(), self.cv2.IMREAD_COLOR if flags == 1 else self.cv2.IMREAD_GRAYSCALE)
