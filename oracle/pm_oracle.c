@@ -903,9 +903,13 @@ int pmo_pick_vertices(const float *costs, const float *geom, int w, int h, int g
 }
 
 /* tris: n_tris x 3 x (x, y) pixel coordinates. planes4: (h, w, 4) result of the previous Run (w = depth).
+ * tri_planes4: the plane of every triangle (n_tris x 4) as the caller fitted it -- the reference's own fit is cv::SVD::solveZ
+ * (:743), which lives in OpenCV, so the faithful caller passes OpenCV's results -- or NULL for the closed form below (the
+ * plane through the three points in double: the same null space, without the float32 SVD's rounding noise; what bench.py's
+ * reference arm times, in the reference's favour).
  * Writes prior4 (h, w, 4) and mask (h, w); returns the number of prior pixels. */
-int pmo_prior_from_triangles(const int *tris, int n_tris, const float *planes4, const float *K, int w, int h, float depth_min,
-                             float depth_max, float *prior4, uint32_t *mask) {
+int pmo_prior_from_triangles_fit(const int *tris, int n_tris, const float *tri_planes4, const float *planes4, const float *K, int w, int h,
+                                 float depth_min, float depth_max, float *prior4, uint32_t *mask) {
     float *fmask = (float *)calloc((size_t)w * h, sizeof(float));
     f4 *tp = (f4 *)malloc(sizeof(f4) * (size_t)(n_tris > 0 ? n_tris : 1));
     const float fx = K[0], fy = K[4], cx = K[2], cy = K[5];
@@ -934,6 +938,7 @@ int pmo_prior_from_triangles(const int *tris, int n_tris, const float *planes4, 
         double nn = sqrt(nx * nx + ny * ny + nz * nz), d = -(nx * X[0][0] + ny * X[0][1] + nz * X[0][2]);
         if (d < 0) nn = -nn; /* :746-749 */
         tp[t].x = (float)(nx / nn); tp[t].y = (float)(ny / nn); tp[t].z = (float)(nz / nn); tp[t].w = (float)(d / nn);
+        if (tri_planes4) memcpy(&tp[t], tri_planes4 + 4 * (size_t)t, sizeof(f4));
     }
     int count = 0;
     for (int j = 0; j < h; ++j)
@@ -952,4 +957,9 @@ int pmo_prior_from_triangles(const int *tris, int n_tris, const float *planes4, 
         }
     free(fmask); free(tp);
     return count;
+}
+
+int pmo_prior_from_triangles(const int *tris, int n_tris, const float *planes4, const float *K, int w, int h, float depth_min,
+                             float depth_max, float *prior4, uint32_t *mask) {
+    return pmo_prior_from_triangles_fit(tris, n_tris, NULL, planes4, K, w, h, depth_min, depth_max, prior4, mask);
 }

@@ -141,9 +141,12 @@ def build_prior(planes_world, costs, K, depth_min, depth_max, geom_costs=None, t
 
 
 # ----------------------------------------------------------------------------- fast path (C loops in libpm_oracle.so)
-def build_prior_fast(planes_world, costs, K, depth_min, depth_max, geom_costs=None):
-    """Same stage with the loops in C (oracle/pm_oracle.c: pmo_pick_vertices, pmo_prior_from_triangles) and OpenCV's
-    Subdiv2D for the triangulation: what bench.py's reference arm runs as the reference pipeline's host stage."""
+def build_prior_fast(planes_world, costs, K, depth_min, depth_max, geom_costs=None, plane_fit="closed"):
+    """Same stage with the loops in C (oracle/pm_oracle.c: pmo_pick_vertices, pmo_prior_from_triangles_fit) and OpenCV's
+    Subdiv2D for the triangulation. plane_fit="closed": the plane through the three vertices in double -- what bench.py's
+    reference arm runs as the reference pipeline's host stage (no 545 k SVD calls: in the reference's favour);
+    plane_fit="svd": every triangle's plane from cv2.SVDecomp as in build_prior -- the reference's own fit, bit for bit
+    (tests/test_reference_program.py) -- for whole-scene comparisons (tests/tools/scene_parity.py)."""
     import ctypes as C
     import os
 
@@ -168,8 +171,14 @@ def build_prior_fast(planes_world, costs, K, depth_min, depth_max, geom_costs=No
     prior = np.zeros((h, w, 4), np.float32)
     mask = np.zeros((h, w), np.uint32)
     Kf = np.ascontiguousarray(np.asarray(K, np.float32).reshape(9))
-    lib.pmo_prior_from_triangles.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float,
-                                             C.c_void_p, C.c_void_p]
-    cnt = lib.pmo_prior_from_triangles(tris.ctypes.data, len(tris), planes_world.ctypes.data, Kf.ctypes.data, w, h,
-                                       C.c_float(depth_min), C.c_float(depth_max), prior.ctypes.data, mask.ctypes.data)
+    tri_planes = None
+    if plane_fit == "svd":
+        K33 = np.asarray(K, np.float32).reshape(3, 3)
+        depth = planes_world[..., 3]
+        tri_planes = np.ascontiguousarray(np.array([plane_from_triangle(t, depth, K33) for t in tris], np.float32).reshape(-1, 4))
+    lib.pmo_prior_from_triangles_fit.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float,
+                                                 C.c_void_p, C.c_void_p]
+    cnt = lib.pmo_prior_from_triangles_fit(tris.ctypes.data, len(tris), None if tri_planes is None else tri_planes.ctypes.data,
+                                           planes_world.ctypes.data, Kf.ctypes.data, w, h, C.c_float(depth_min), C.c_float(depth_max),
+                                           prior.ctypes.data, mask.ctypes.data)
     return prior, mask, verts, tris, cnt

@@ -135,6 +135,29 @@ def test_prior_restatement_reproduces_the_reference_programs_prior(name):
 
 
 @pytest.mark.parametrize("name", ["planar", "geom_planar"])
+def test_c_restatement_reproduces_the_reference_programs_prior(name):
+    """The same for the C loops that whole-scene comparisons and bench.py's reference arm run (oracle/pm_oracle.c through
+    prior_oracle.build_prior_fast): with OpenCV's SVD per triangle (plane_fit="svd", what tests/tools/scene_parity.py uses) the
+    reference's prior bit for bit; with the closed-form plane (what the bench arm times) the same triangle ids and planes
+    within the SVD's float32 noise."""
+    import prior_oracle
+
+    c = prior_cases()[name]
+    cam = c["cams"][0]
+    K = np.asarray(cam["K"], np.float32).reshape(3, 3)
+    dmin, dmax = float(np.float32(cam["depth_min"]) * np.float32(0.6)), float(np.float32(cam["depth_max"]) * np.float32(1.2))
+    on = c["mask"] > 0
+    prior, mask, _, _, cnt = prior_oracle.build_prior_fast(c["in_planes"], c["in_costs"], K, dmin, dmax, c["in_geom"], plane_fit="svd")
+    np.testing.assert_array_equal(mask, c["mask"])
+    np.testing.assert_array_equal(prior[on], c["planes"][on])
+    assert cnt == int(on.sum())
+    prior, mask, _, _, _ = prior_oracle.build_prior_fast(c["in_planes"], c["in_costs"], K, dmin, dmax, c["in_geom"], plane_fit="closed")
+    assert (mask == c["mask"]).mean() > 0.9995
+    both = (mask == c["mask"]) & on
+    assert np.abs(prior[both] - c["planes"][both]).max() < 2e-3
+
+
+@pytest.mark.parametrize("name", ["planar", "geom_planar"])
 def test_product_triangulation_on_the_reference_programs_state(name):
     """Host part of the product's prior stage on the same state: the restated vertex picking feeds mpmvs_delaunay; every
     triangle id the reference rasterised must be one of its list (same order => same ids)."""

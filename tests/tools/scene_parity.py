@@ -36,6 +36,7 @@ ap.add_argument("--arithmetic", default="exact", choices=["exact", "fast"])
 ap.add_argument("--tex", default=None)
 ap.add_argument("--order", default="jacobi", choices=["jacobi", "gauss_seidel"])
 ap.add_argument("--share-prior", action="store_true", help="the reference run uses the priors our planar-prior stage built")
+ap.add_argument("--plane-fit", default="svd", choices=["svd", "closed"], help="the reference side's plane fit: cv2's SVD per triangle (the reference's own, default) or the closed form")
 ap.add_argument("--skip-reference", action="store_true")
 ap.add_argument("--in-flight", type=int, default=8)
 ap.add_argument("--out", default=None)
@@ -99,7 +100,7 @@ if not args.skip_reference and oracle_py.available("ref"):
                 prior_turn[ref_id] += 1
             else:
                 dmin, dmax = R.depth_range
-                prior, mask, _, _, _ = prior_oracle.build_prior_fast(res[0], res[1], sc.cams[ref_id].K, dmin, dmax, res[2] if geom else None)
+                prior, mask, _, _, _ = prior_oracle.build_prior_fast(res[0], res[1], sc.cams[ref_id].K, dmin, dmax, res[2] if geom else None, plane_fit=args.plane_fit)
             R.set_planar_prior_params()
             R.set_geom_consistency_params(False, True)
             R.set_prior(prior, mask)
