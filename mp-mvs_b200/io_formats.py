@@ -79,10 +79,12 @@ class Camera:
 
     @property
     def C(self) -> np.ndarray:
-        # PatchMatch.cpp:134-136, C = -R^T t evaluated in float32 like the reference.
+        # PatchMatch.cpp:134-136: C[k] = -(R[k] t[0] + R[3+k] t[1] + R[6+k] t[2]) in float32, every product and sum rounded, left to
+        # right (a BLAS matrix product may fuse or reorder them: the last bit of C reaches every homography).
         R = self.R.astype(np.float32)
         t = self.t.astype(np.float32)
-        return (-(R.T @ t)).astype(np.float32)
+        f = np.float32
+        return np.array([-f(f(f(R[0, k] * t[0]) + f(R[1, k] * t[1])) + f(R[2, k] * t[2])) for k in range(3)], dtype=np.float32)
 
     def pack(self) -> np.ndarray:
         """112-byte record laid out exactly like the C struct."""

@@ -37,11 +37,10 @@ def block_size(n_refs: int, world: int) -> int:
 
 
 def stage_seed(seed: int, ref_id: int, stage: int) -> int:
-    """Per (image, pass) seed, independent of the rank that runs it."""
-    z = (seed + 0x9E3779B97F4A7C15 * (ref_id * 64 + stage + 1)) & 0xFFFFFFFFFFFFFFFF
-    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
-    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
-    return z ^ (z >> 31)
+    """Per (image, pass) seed, independent of the rank that runs it -- the C++ host's convention (mpmvs_main.cpp: seed +
+    1000003 i + 7919 stage, the planar-prior Run() of a pass XORs 0x5DEECE66D), so both hosts draw the same random numbers
+    for the same --seed (the library mixes the seed with the pixel position, pm_rng_init)."""
+    return (seed + 1000003 * ref_id + 7919 * stage) & 0xFFFFFFFFFFFFFFFF
 
 
 @dataclass

@@ -25,6 +25,20 @@ pkgload.load_package()
 from mpmvs_b200 import io_formats, pipeline, previews  # noqa: E402
 
 
+def cv_resize(img, size):
+    """cv::resize(INTER_LINEAR) as OpenCV itself computes it. Where the cv2 build has Intel IPP, IPP's resize answers up to 3e-3
+    grey levels (float) / one level (8 bit) differently; the C++ host's resizes are OpenCV's own paths bit for bit
+    (mpmvs_host.cpp: resizeLinear, resizeLinearBGR), so IPP is switched off for the call and both hosts see the same pixels."""
+    import cv2
+
+    ipp = cv2.ipp.useIPP()
+    cv2.ipp.setUseIPP(False)
+    try:
+        return cv2.resize(img, size, interpolation=cv2.INTER_LINEAR)
+    finally:
+        cv2.ipp.setUseIPP(ipp)
+
+
 def load_image(folder: str, image_id: int, max_size: int):
     """PatchMatchInit's loading rule (PatchMatch.cpp:871-925): grey uint8 -> float32, cv::resize(INTER_LINEAR) above
     `max_size`. Returns (image, scale_x, scale_y); the image stays uint8 when it was not resized."""
@@ -39,7 +53,7 @@ def load_image(folder: str, image_id: int, max_size: int):
         return img, 1.0, 1.0
     factor = min(np.float32(max_size) / np.float32(w), np.float32(max_size) / np.float32(h))
     nw, nh = int(round(float(np.float32(w) * factor))), int(round(float(np.float32(h) * factor)))
-    out = cv2.resize(img.astype(np.float32), (nw, nh), interpolation=cv2.INTER_LINEAR)
+    out = cv_resize(img.astype(np.float32), (nw, nh))
     return out, nw / np.float32(w), nh / np.float32(h)
 
 
@@ -52,7 +66,7 @@ def load_color(folder: str, image_id: int, shape):
     if bgr is None:
         return None
     if bgr.shape[:2] != tuple(shape):
-        bgr = cv2.resize(bgr, (shape[1], shape[0]), interpolation=cv2.INTER_LINEAR)
+        bgr = cv_resize(bgr, (shape[1], shape[0]))
     return bgr
 
 
@@ -196,6 +210,10 @@ def main():
     ap.add_argument("--seed", type=int, default=0x2333)
     ap.add_argument("--in-flight", type=int, default=8, help="reference images in flight per GPU (host threads: the planar-prior triangulation is host work)")
     ap.add_argument("--fusion", type=int, default=1, help="fuse the depth maps on rank 0's GPU and write MPMVS_model.ply")
+    ap.add_argument("--order", default="jacobi", choices=["jacobi", "gauss_seidel"],
+                    help="jacobi (default): a geometric pass reads the previous pass's depth maps, results independent of the number of "
+                         "GPUs; gauss_seidel (one GPU): the reference's in-place order (src/PatchMatch.cpp:620-633) -- with the exact "
+                         "arithmetic the .dmb files are then byte-identical to the reference's and to mpmvs_main's for the same --seed")
     ap.add_argument("--arithmetic", "--fidelity", dest="arithmetic", default="exact", choices=["exact", "fast"],
                     help="exact (default): the reference's kernel results bit for bit, float32 view storage; fast: the library's "
                          "hoisted arithmetic with 8-bit view storage, statistically equal results (mpmvs_set_arithmetic)")
@@ -219,7 +237,7 @@ def main():
                                    seed=args.seed, planar_prior=bool(int(cfg["Planer prior"])),
                                    geom_planar_prior=bool(int(cfg["Geometric consistency planer prior"])),
                                    tex_format=capi.TEX_F32 if (resized or args.arithmetic == "exact") else capi.TEX_U8, in_flight=args.in_flight,
-                                   arithmetic=args.arithmetic)
+                                   arithmetic=args.arithmetic, order=args.order)
     p = pipeline.DensePipeline(entries, cams, images, pcfg, rank=rank, world=world, device=local, dist=dist)
     p.setup()
     t1 = time.time()

@@ -4,6 +4,8 @@ GPU parity tests). Every case is a (scene, reference view) problem small enough 
 Inputs are rendered by mpmvs_b200.synth (deterministic numpy); the golden files additionally store the uint8 images
 so the fixtures do not depend on the renderer staying bit-stable.
 """
+import os
+
 import numpy as np
 
 from conftest import PKG, gt_planes_cam, problem_arrays
@@ -25,7 +27,15 @@ def make_case(name):
     else:
         raise KeyError(name)
     ids, imgs, cams = problem_arrays(sc, ref)
-    return dict(name=name, scene=sc, ref=ref, ids=ids, images=imgs, cams=cams)
+    # The golden outputs were computed (by the reference, on a B200) from the camera records stored next to them. Those records hold
+    # the camera centre C as a BLAS product evaluated it in round 1; io_formats.Camera.C now follows ReadCamera's own order of
+    # operations (PatchMatch.cpp:134-136) and differs from that in the last bit for some cameras -- either is a legitimate input,
+    # but the outputs belong to the stored one.
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz")
+    rendered = cams
+    if os.path.exists(gold):
+        cams = np.load(gold)["cams"]
+    return dict(name=name, scene=sc, ref=ref, ids=ids, images=imgs, cams=cams, cams_rendered=rendered)
 
 
 CASES = ("plane3", "dtu5", "room6")

@@ -206,13 +206,14 @@ def test_gpu_prior_stage_against_the_reference_programs_prior(name):
 @pytest.mark.gpu
 @pytest.mark.skipif(not ref_host.available(), reason="oracle/_ref/libmpmvs_ref_host.so not built on this box")
 def test_whole_program_against_the_references_main():
-    """The reference's main() and the product's mpmvs_main on the same dense folder, same seeds (9 views, 320x240):
+    """The reference's main() and the product's hosts -- mpmvs_main (C++) and run.py (Python, --order gauss_seidel) -- on the same
+    dense folder, same seeds (9 views, 320x240):
     * photometric + 2 geometric passes + fusion; a pair.txt that exercises GenerateSampleList's rules; images above `Max image
       size`: every depths / normals / costs .dmb and MPMVS_model.ply BYTE-IDENTICAL;
     * the two schedules with a planar prior: the product's prior has the reference's triangle id on every pixel and its planes
       within float32-SVD noise; the depth maps are then no longer bit-identical (that noise, amplified by the propagation)
       but agree on > 90 % of the pixels at 1 % depth / 5 degrees (measured 97.8 / 94.8 % median), with the same accuracy."""
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "reference_program.py"), "--schedules", "photo_geom,quirks,resized,planar,geom_planar"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "reference_program.py"), "--schedules", "photo_geom,quirks,resized,planar,geom_planar", "--python-host"],
                        capture_output=True, text=True, timeout=1800)
     assert r.returncode == 0, r.stderr[-3000:]
     res = json.loads(r.stdout.strip().splitlines()[-1])["schedules"]
@@ -223,6 +224,8 @@ def test_whole_program_against_the_references_main():
     for name in ("photo_geom", "quirks", "resized"):
         a = res[name]
         assert a["depth_maps_byte_identical"] == n and a["normal_maps_byte_identical"] == n and a["cost_maps_byte_identical"] == n and a["ply_byte_identical"], a
+        b = a["python_host"]       # mp-mvs_b200/run.py --order gauss_seidel: the Python host writes the same maps (its fusion runs on the GPU)
+        assert b["depth_maps_byte_identical"] == n and b["normal_maps_byte_identical"] == n and b["cost_maps_byte_identical"] == n, b
     for name in ("planar", "geom_planar"):
         b = res[name]
         assert b["reference_priors_captured"] == n

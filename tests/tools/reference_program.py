@@ -86,7 +86,8 @@ def read_results(dense, n):
     for i in range(n):
         d = os.path.join(dense, "MPMVS", f"2333_{i:08d}")
         out.append({k: open(os.path.join(d, k + ".dmb"), "rb").read() for k in ("depths", "normals", "costs")})
-    ply = open(os.path.join(dense, "MPMVS", "MPMVS_model.ply"), "rb").read()
+    path = os.path.join(dense, "MPMVS", "MPMVS_model.ply")
+    ply = open(path, "rb").read() if os.path.exists(path) else b""
     return out, ply
 
 
@@ -133,6 +134,8 @@ if __name__ == "__main__":
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--svd-noise", action="store_true", help="also run the reference with another SVD behind cv::SVD::solveZ (numpy, float64) "
                     "and report reference-against-reference agreement: how much of a difference is the plane fit's rounding noise")
+    ap.add_argument("--python-host", action="store_true", help="also run the Python host (mp-mvs_b200/run.py --order gauss_seidel, no fusion) and "
+                    "compare its .dmb files with the reference's")
     ap.add_argument("--priors", type=int, default=3, help="how many of the captured priors to compare with the product's stage")
     ap.add_argument("--schedules", default="photo_geom,planar,geom_planar")
     ap.add_argument("--seed", type=int, default=7)
@@ -152,7 +155,7 @@ if __name__ == "__main__":
     for name in a.schedules.split(","):
         cfg = dict({"Max source images num": max_src}, **SCHEDULES[name])
         sides = {}
-        for side in ("reference", "ours") + (("reference_other_svd",) if a.svd_noise and (cfg["Planer prior"] or cfg["Geometric consistency planer prior"]) else ()):   # noqa: E501
+        for side in ("reference", "ours") + (("reference_other_svd",) if a.svd_noise and (cfg["Planer prior"] or cfg["Geometric consistency planer prior"]) else ()) + (("python_host",) if a.python_host else ()):   # noqa: E501
             proj = os.path.join(work, name, side)
             shutil.rmtree(proj, ignore_errors=True)
             dense = os.path.join(proj, "dense")
@@ -167,6 +170,11 @@ if __name__ == "__main__":
                 cap = os.path.join(proj, "priors.npz")
                 log = ref_host.run_main(proj, seed=a.seed, capture=cap, timeout=6000, solvez="cv2" if side == "reference" else "numpy64",
                                         ipp=name != "resized")
+            elif side == "python_host":
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "mp-mvs_b200", "run.py"), yaml, "--seed", str(a.seed), "--order", "gauss_seidel",
+                                    "--fusion", "0", "--arithmetic", "exact"], capture_output=True, text=True, timeout=6000)
+                assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+                log = r.stdout
             else:
                 r = subprocess.run([MAIN, yaml, "--seed", str(a.seed), "--tex", "f32", "--arithmetic", "exact"], capture_output=True, text=True, timeout=6000)
                 assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
@@ -199,6 +207,10 @@ if __name__ == "__main__":
 
         if not all(ident["depths"]):      # how close, where not identical
             entry["agreement_median_min"], entry["accuracy_2cm_reference_ours"] = closeness(ra, oa)
+        if "python_host" in sides:           # the Python host in the reference's order: same seeds, same files
+            pa, _ = sides["python_host"]["results"]
+            entry["python_host"] = {k + "_maps_byte_identical": int(sum(x[k + "s"] == y[k + "s"] for x, y in zip(ra, pa))) for k in ("depth", "normal", "cost")}
+            entry["python_host"]["wall_s"] = sides["python_host"]["wall_s"]
         if "reference_other_svd" in sides:   # the reference against itself with another SVD behind cv::SVD::solveZ
             rb, _ = sides["reference_other_svd"]["results"]
             entry["reference_vs_reference_other_svd"] = {"depth_maps_byte_identical": int(sum(x["depths"] == y["depths"] for x, y in zip(ra, rb)))}
