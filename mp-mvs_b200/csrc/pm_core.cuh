@@ -277,7 +277,7 @@ PM_HD float pm_dot3(const pm_f4& a, const pm_f4& b) {
 // not always 1 when the two focal lengths are equal), so it is formed here and not on the host.
 //
 // Exact arithmetic: nvcc contracts the reference's three-term denominator in TWO ways depending on the inlined copy
-// (SASS of oracle/_ref, BlackPixelUpdate / RedPixelUpdate; tests/tools/sass_dag.py lists them):
+// (SASS of oracle/_ref, BlackPixelUpdate / RedPixelUpdate; tests/tools/sass_expr.py compares them):
 //   form 0, every copy but one:            FFMA(fx, nz, FFMA(nx, x - cx,  FMUL(ny, yt)))     yt = (fx * RCP(fy)) * (y - cy)
 //   form 1, ComputeGeomConsistencyCost's copy inside PlaneHypothesisRefinement (cu:687):
 //                                          FFMA(fx, nz, FFMA(ny, yt,      FMUL(x - cx, nx)))
