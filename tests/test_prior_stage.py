@@ -78,6 +78,25 @@ def test_triangle_list_is_opencvs(kind):
     np.testing.assert_array_equal(ours, want)
 
 
+def test_triangle_list_fuzz_against_opencv():
+    """400 small random sets, three quarters of them degenerate on purpose (lattices: collinear, co-circular and repeated points;
+    almost everything on one line; a tiny dense cluster): the list is OpenCV's every time (3 000 such cases were run once)."""
+    rng = np.random.default_rng(12345)
+    for it in range(400):
+        w, h, n = int(rng.integers(8, 60)), int(rng.integers(8, 60)), int(rng.integers(3, 80))
+        kind = it % 4
+        if kind == 0:
+            pts = np.stack([rng.integers(0, w, n), rng.integers(0, h, n)], 1)
+        elif kind == 1:
+            pts = np.stack([rng.integers(0, w, n) // 3 * 3, rng.integers(0, h, n) // 3 * 3], 1)
+        elif kind == 2:
+            pts = np.stack([rng.integers(0, w, n), np.full(n, rng.integers(0, h))], 1)
+            pts[::5, 1] = rng.integers(0, h, len(pts[::5]))
+        else:
+            pts = np.stack([rng.integers(0, min(w, 6), n), rng.integers(0, min(h, 6), n)], 1)
+        np.testing.assert_array_equal(our_triangle_list(pts, w, h), cv_triangle_list(pts, w, h), err_msg=f"case {it}")
+
+
 def test_delaunay_edge_cases():
     assert len(capi.delaunay(np.zeros((0, 2), np.int32), 10, 10)) == 0
     assert len(capi.delaunay(np.array([(1, 1), (5, 5)], np.int32), 10, 10)) == 0
