@@ -209,7 +209,10 @@ def main():
     ap.add_argument("config")
     ap.add_argument("--seed", type=int, default=0x2333)
     ap.add_argument("--in-flight", type=int, default=8, help="reference images in flight per GPU (host threads: the planar-prior triangulation is host work)")
-    ap.add_argument("--fusion", type=int, default=1, help="fuse the depth maps on rank 0's GPU and write MPMVS_model.ply")
+    ap.add_argument("--fusion", type=int, default=1, choices=[0, 1, 2],
+                    help="1 (default): fuse the depth maps on rank 0's GPU (image-parallel kernels) and write MPMVS_model.ply; 2: the reference's "
+                         "sequential host order through the C++ host (mpmvs_main --fusion-only): the reference's .ply byte for byte, "
+                         "single-threaded; 0: no fusion")
     ap.add_argument("--order", default="jacobi", choices=["jacobi", "gauss_seidel"],
                     help="jacobi (default): a geometric pass reads the previous pass's depth maps, results independent of the number of "
                          "GPUs; gauss_seidel (one GPU): the reference's in-place order (src/PatchMatch.cpp:620-633) -- with the exact "
@@ -263,7 +266,20 @@ def main():
     t4 = t3
     n_points = None
     p.destroy()            # the resident PatchMatch state (76 B/px per reference image) is not needed any more: free it before fusion
-    if rank == 0 and args.fusion:
+    if rank == 0 and args.fusion == 2:
+        # RunFusion in the reference's own pixel order (a later pixel sees the masks earlier ones set, PatchMatch.cpp:374-499): host code,
+        # which lives in the C++ host; it reads the .dmb files every rank has written
+        import subprocess
+
+        exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "mpmvs_main")
+        if not os.path.exists(exe):
+            raise FileNotFoundError(f"{exe}: build it with `make -C mp-mvs_b200/csrc`")
+        r = subprocess.run([exe, args.config, "--fusion-only"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("mpmvs_main --fusion-only failed:\n" + r.stdout[-2000:] + r.stderr[-2000:])
+        n_points = int(r.stdout.split("store 3D points to ply file: ")[1].split(" points")[0])
+        t4 = time.time()
+    elif rank == 0 and args.fusion:
         # RunFusion (PatchMatch.cpp:287-504) on the GPU: every rank has written its maps, rank 0 reads them back
         est = sorted(e.ref_id for e in entries if e.estimate)
         by_ref = {e.ref_id: e for e in entries if e.estimate}
@@ -294,7 +310,7 @@ def main():
               f"({[(s.name, round(s.device_ms)) for s in stats]}), write {t3 - t2:.2f} s on {world} GPU(s)")
         print(f"cost time is {(t2 - t1) * 1e6:.10f} us")
         if n_points is not None:
-            print(f"fusion: {n_points} points in {t4 - t3:.2f} s (load + GPU fusion + ply)")
+            print(f"fusion: {n_points} points in {t4 - t3:.2f} s ({'host, reference order' if args.fusion == 2 else 'load + GPU fusion'} + ply)")
     if dist is not None:
         dist.destroy_process_group()
 

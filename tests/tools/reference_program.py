@@ -134,8 +134,8 @@ if __name__ == "__main__":
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--svd-noise", action="store_true", help="also run the reference with another SVD behind cv::SVD::solveZ (numpy, float64) "
                     "and report reference-against-reference agreement: how much of a difference is the plane fit's rounding noise")
-    ap.add_argument("--python-host", action="store_true", help="also run the Python host (mp-mvs_b200/run.py --order gauss_seidel, no fusion) and "
-                    "compare its .dmb files with the reference's")
+    ap.add_argument("--python-host", action="store_true", help="also run the Python host (mp-mvs_b200/run.py --order gauss_seidel --fusion 2) and "
+                    "compare its files with the reference's")
     ap.add_argument("--priors", type=int, default=3, help="how many of the captured priors to compare with the product's stage")
     ap.add_argument("--schedules", default="photo_geom,planar,geom_planar")
     ap.add_argument("--seed", type=int, default=7)
@@ -172,7 +172,7 @@ if __name__ == "__main__":
                                         ipp=name != "resized")
             elif side == "python_host":
                 r = subprocess.run([sys.executable, os.path.join(ROOT, "mp-mvs_b200", "run.py"), yaml, "--seed", str(a.seed), "--order", "gauss_seidel",
-                                    "--fusion", "0", "--arithmetic", "exact"], capture_output=True, text=True, timeout=6000)
+                                    "--fusion", "2", "--arithmetic", "exact"], capture_output=True, text=True, timeout=6000)
                 assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
                 log = r.stdout
             else:
@@ -210,6 +210,7 @@ if __name__ == "__main__":
         if "python_host" in sides:           # the Python host in the reference's order: same seeds, same files
             pa, _ = sides["python_host"]["results"]
             entry["python_host"] = {k + "_maps_byte_identical": int(sum(x[k + "s"] == y[k + "s"] for x, y in zip(ra, pa))) for k in ("depth", "normal", "cost")}
+            entry["python_host"]["ply_byte_identical"] = bool(sides["python_host"]["results"][1] == rply)
             entry["python_host"]["wall_s"] = sides["python_host"]["wall_s"]
         if "reference_other_svd" in sides:   # the reference against itself with another SVD behind cv::SVD::solveZ
             rb, _ = sides["reference_other_svd"]["results"]
